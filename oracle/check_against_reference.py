@@ -1,0 +1,150 @@
+"""Pin the oracle against the reference's own Python files and emit golden vectors.
+
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs
+``/root/reference``); the GPU box never executes this file.
+
+What it does
+  1. injects two shim modules, ``fairseq`` and ``conformer`` (the reference's
+     un-vendored third-party imports), backed by the oracle's restatements;
+  2. imports the reference's ``models/xlsr_aasist.py``, ``models/conformer_baseline.py``,
+     ``models/fe.py``, ``models/aasist_modules.py`` and ``data/preprocess.py``
+     UNMODIFIED from ``/root/reference`` and runs them on CPU;
+  3. loads the same state dict into the oracle's restated classes and asserts
+     equal outputs (max |diff| printed; threshold 2e-5);
+  4. writes ``tests/golden/*.npz``: seeds, shapes and the *reference's* outputs,
+     which the tests compare the oracle and the CUDA path against.
+
+Usage:  python -m oracle.check_against_reference [--write]
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def install_shims():
+    from oracle.conformer_block_ref import ConformerBlock
+    from oracle.wav2vec2_ref import FairseqLikeWav2Vec2
+
+    fairseq = types.ModuleType("fairseq")
+    cu = types.ModuleType("fairseq.checkpoint_utils")
+
+    def load_model_ensemble_and_task(paths, *a, **k):
+        return [FairseqLikeWav2Vec2()], None, None
+
+    cu.load_model_ensemble_and_task = load_model_ensemble_and_task
+    fairseq.checkpoint_utils = cu
+    sys.modules["fairseq"] = fairseq
+    sys.modules["fairseq.checkpoint_utils"] = cu
+    conformer = types.ModuleType("conformer")
+    conformer.ConformerBlock = ConformerBlock
+    sys.modules["conformer"] = conformer
+    cfg = types.ModuleType("config")  # data/preprocess.py does `import config`; nothing of it is used
+    sys.modules.setdefault("config", cfg)
+
+
+def import_reference():
+    install_shims()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    xa = importlib.import_module("models.xlsr_aasist")
+    cb = importlib.import_module("models.conformer_baseline")
+    pp = importlib.import_module("data.preprocess")
+    return xa, cb, pp
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--write", action="store_true", help="write tests/golden/*.npz")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    xa, cb, pp = import_reference()
+    from oracle import models_ref as O
+    from oracle.aasist_ref import perturb_norm_stats
+
+    results = {}
+    worst = 0.0
+
+    def ref_build(cls, seed, **kw):
+        torch.manual_seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = cls("cpu", None, **kw).eval()
+        perturb_norm_stats(m, seed=seed + 1)
+        return m
+
+    cases = [
+        # name, reference class, oracle kind, kwargs, B, N
+        ("xlsr_aasist_n16000_b2", xa.XLSR_AASIST, "XLSR_AASIST", {}, 2, 16000),
+        ("xlsr_aasist_n64000_b2", xa.XLSR_AASIST, "XLSR_AASIST", {}, 2, 64000),
+        ("xlsr_aasist_n64600_b1", xa.XLSR_AASIST, "XLSR_AASIST", {}, 1, 64600),
+        ("student6_aasist_n64000_b2", xa.My_XLSR_AASIST, "My_XLSR_AASIST", {"num_layers": 6, "order": "first"}, 2, 64000),
+        ("student_mid4_aasist_n16000_b2", xa.My_XLSR_AASIST, "My_XLSR_AASIST", {"num_layers": 4, "order": "middle"}, 2, 16000),
+        ("conformer_n64600_b1", cb.Model, "ConformerModel", {}, 1, 64600),
+        ("conformer_n16000_b2", cb.Model, "ConformerModel", {}, 2, 16000),
+    ]
+    for name, rcls, okind, kw, B, N in cases:
+        seed = 1024
+        ref = ref_build(rcls, seed, **kw)
+        ora = O.build(okind, seed=seed, **kw)
+        missing = ora.load_state_dict(ref.state_dict(), strict=True)
+        # the two seeded constructions must agree even without the copy
+        x = O.synth_waveforms(B, N, seed=2021)
+        with torch.no_grad():
+            y_ref = ref(x)
+            taps = {}
+            y_ora = ora(x, taps)
+        d = float((y_ref - y_ora).abs().max())
+        worst = max(worst, d)
+        print(f"{name:34s} ref-vs-oracle max|dlogit| = {d:.3e}   logits[0] = {y_ref[0].tolist()}")
+        results[name] = dict(kind=okind, kwargs=repr(kw), seed=seed, wave_seed=2021, B=B, N=N,
+                             logits=y_ref.numpy().astype(np.float32),
+                             feats_head=taps["feats"][:, :4, :16].numpy().astype(np.float32),
+                             feats_absmean=np.float32(taps["feats"].abs().mean()))
+        if "idx_S" in taps:
+            results[name].update(idx_S=taps["idx_S"].numpy().astype(np.int64), idx_T=taps["idx_T"].numpy().astype(np.int64))
+
+    # student Conformer: shipped forward raises TypeError (conformer_baseline.py:98)
+    stu = ref_build(cb.MyModel, 1024, num_layers=2)
+    try:
+        with torch.no_grad():
+            stu(O.synth_waveforms(1, 16000))
+        raise SystemExit("reference MyModel unexpectedly ran")
+    except TypeError as e:
+        print("reference MyModel.forward raises TypeError as documented:", e)
+
+    # pre-emphasis (data/preprocess.py)
+    class _Exp:
+        pre_emphasis = 0.97
+        is_pre_emphasis = True
+    pre = pp.PreEmphasis("cpu", None, _Exp())
+    x = O.synth_waveforms(3, 4000, seed=5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        y_ref = pre(x)
+    d = float((y_ref - O.pre_emphasis(x)).abs().max())
+    worst = max(worst, d)
+    print(f"pre-emphasis ref-vs-oracle max|d| = {d:.3e}")
+    results["preemph_b3_n4000"] = dict(wave_seed=5, B=3, N=4000, out_head=y_ref[:, :64].numpy().astype(np.float32),
+                                       out_sum=np.float64(y_ref.double().sum()))
+
+    assert worst <= 2e-5, f"oracle disagrees with reference: {worst}"
+    print("oracle == reference within 2e-5: OK")
+    if args.write:
+        os.makedirs(GOLDEN, exist_ok=True)
+        for name, d in results.items():
+            np.savez(os.path.join(GOLDEN, name + ".npz"), **d)
+        print("wrote", len(results), "golden files to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()

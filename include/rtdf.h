@@ -1,0 +1,126 @@
+/*
+ * rtdf.h -- C-ABI of librtdf.so: B200-native (sm_100a) batched evaluation-scoring forward for
+ * hungdinhxuan/real-time-deepfake-speech-detection (waveform -> XLS-R -> AASIST | Conformer -> logits).
+ *
+ * The reference has no FFI/plugin layer: its boundary is the nn.Module contract of the model classes
+ * (reference models/xlsr_aasist.py:5-177, models/conformer_baseline.py:31-99, models/fe.py:8-99) as
+ * consumed by main.py:199-221 (produce_evaluation_file) and trainer.py:85-132 (Trainer._test).  The
+ * entry points below are what a binding for that path calls; the Python mirror of the model classes in
+ * real-time-deepfake-speech-detection_b200/models/ binds them with ctypes.
+ *
+ * Conventions: every function returns 0 on success or a negative rtdf_status; the message is available
+ * from rtdf_last_error() (thread-local).  The CALLER owns all input/output/workspace buffers (device
+ * memory); the context owns only packed weights.  All work is enqueued on the caller's stream; there are
+ * no internal synchronisations and no allocations in the forward calls (CUDA-graph capturable).
+ * One context per (device, model instance); a context is not thread-safe.
+ */
+#ifndef RTDF_H_
+#define RTDF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rtdf_ctx rtdf_ctx;
+
+enum rtdf_status {
+  RTDF_STATUS_OK = 0,
+  RTDF_STATUS_INVALID = -1,      /* bad argument / shape                         */
+  RTDF_STATUS_CUDA = -2,         /* CUDA runtime / driver error                  */
+  RTDF_STATUS_STATE = -3,        /* call order violated (e.g. not finalized)     */
+  RTDF_STATUS_UNSUPPORTED = -4   /* configuration outside the implemented path   */
+};
+
+enum rtdf_backend { RTDF_BACKEND_AASIST = 0, RTDF_BACKEND_CONFORMER = 1, RTDF_BACKEND_NONE = 2 };
+enum rtdf_precision {
+  RTDF_PREC_BF16 = 0,            /* tcgen05 bf16 x bf16 -> fp32 GEMMs, fp32 residual stream / statistics */
+  RTDF_PREC_FP32 = 1             /* FFMA-only verification mode (max |logit diff| <= 1e-4)               */
+};
+
+/* Architecture of one model instance.  Mirrors the reference constructors' kwargs:
+ * num_layers (models/fe.py:57), emb_size / heads / kernel_size / n_encoders
+ * (models/conformer_baseline.py:38-41). */
+typedef struct rtdf_model_desc {
+  int backend;        /* rtdf_backend                                               */
+  int n_layers;       /* transformer layers kept in ssl_model.model.encoder.layers  */
+  int precision;      /* rtdf_precision                                             */
+  int conf_emb;       /* Conformer: emb_size (144)                                  */
+  int conf_heads;     /* Conformer: heads (4)                                       */
+  int conf_kernel;    /* Conformer: depth-wise conv kernel size (31)                */
+  int conf_blocks;    /* Conformer: n_encoders (4)                                  */
+  int attention_impl; /* 0 = tcgen05 tile kernel, 1 = SIMT kernel (debug)           */
+} rtdf_model_desc;
+
+/* Optional intermediate outputs of a forward call (device pointers, may be NULL). */
+typedef struct rtdf_taps {
+  float* feats;    /* (B, T, 1024) XLS-R output features (fe.py:17-21 'x')          */
+  float* hidden;   /* (B, 160) AASIST read-out vector (xlsr_aasist.py:171-172)      */
+  int32_t* idx_S;  /* (B, 21)  nodes kept by pool_S, descending score               */
+  int32_t* idx_T;  /* (B, T'/2) nodes kept by pool_T                                */
+} rtdf_taps;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc);
+/* Copies one state-dict entry (fp32, device OR host pointer, contiguous) into the context.  `key` is the
+ * reference state-dict key without any "module." prefix (utils.py:13-43), e.g.
+ * "ssl_model.model.encoder.layers.3.fc1.weight".  Unknown keys are stored and ignored. */
+int rtdf_load_weight(rtdf_ctx* ctx, const char* key, const void* data, const int64_t* shape, int ndim);
+/* Packs weights: bf16 casts, fused QKV (1/8 folded into W_q, b_q), weight-norm fold of pos_conv,
+ * eval-BatchNorm folds, implicit-GEMM conv weight layout.  Fails listing the first missing key. */
+int rtdf_finalize(rtdf_ctx* ctx);
+void rtdf_destroy(rtdf_ctx* ctx);
+const char* rtdf_last_error(void);
+
+/* ---- scoring forward ------------------------------------------------------------------------- */
+/* Number of frames T for an N-sample utterance (7 strided convs). */
+int rtdf_num_frames(int n_samples);
+int rtdf_workspace_bytes(const rtdf_ctx* ctx, int batch, int n_samples, size_t* out);
+/* wav: (B,N) fp32 device.  preemph != 0 applies y[t] = x[t] - coef*x[t-1] first (data/preprocess.py:22-27;
+ * used by trainer.py:104, not by main.py:208-214).  logits: (B,2) fp32 device.  stream: cudaStream_t. */
+int rtdf_forward(rtdf_ctx* ctx, const float* wav, int batch, int n_samples, int preemph, float preemph_coef,
+                 float* logits, void* workspace, size_t workspace_bytes, const rtdf_taps* taps, void* stream);
+/* Front-end only: wav -> feats (B,T,1024) fp32   (XLSR_FE.extract_feat, models/fe.py:17-21). */
+int rtdf_frontend(rtdf_ctx* ctx, const float* wav, int batch, int n_samples, int preemph, float preemph_coef,
+                  float* feats, void* workspace, size_t workspace_bytes, void* stream);
+/* Back-end only: feats (B,T,1024) fp32 -> logits (B,2). */
+int rtdf_backend(rtdf_ctx* ctx, const float* feats, int batch, int n_frames, float* logits, void* workspace,
+                 size_t workspace_bytes, const rtdf_taps* taps, void* stream);
+
+/* ---- single kernels (unit parity tests; all pointers are device pointers) --------------------- */
+int rtdf_preemph(const float* x, float* y, int batch, int n, float coef, void* stream);
+int rtdf_wave_layernorm(const float* x, float* y, int batch, int n, float eps, void* stream);
+int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w_tapmajor /*[10][512]*/, const float* bias,
+                       const float* gamma, const float* beta, float eps, float* out_f32 /*or NULL*/,
+                       void* out_bf16 /*or NULL*/, void* stream);
+int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
+                        const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream);
+/* D = act(A W^T + bias) * scale + resid.  A: (M,K) bf16, W: (N,K) bf16.  variant: tile width 64|128|256. */
+int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const float* bias, int act, float scale,
+                   const float* resid, float* out_f32, void* out_bf16, int variant, void* stream);
+int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const float* bias, int act, float scale,
+                  const float* resid, float* out_f32, void* stream);
+/* Strided 1-D conv as implicit GEMM on channels-last bf16 activations, fused bias + LayerNorm(512) + GELU:
+ * x (B, L_in, 512) -> y (B, L_out, 512), w packed [512][k][512] bf16.  variant 512 (BK 64) | 513 (BK 32). */
+int rtdf_conv1d_ln_gelu_bf16(const void* x, int batch, int l_in, int k, int stride, const void* w_packed,
+                             const float* bias, const float* gamma, const float* beta, float eps, void* y,
+                             int variant, void* stream);
+/* Grouped positional conv (k=128, groups=16, pad 64, last frame dropped) + GELU + residual:
+ * x_f32 (B,T,1024) += gelu(conv(x_bf16) + bias).  w packed [1024][128*64] bf16 (k index = tap*64 + ci). */
+int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames, const void* w_packed,
+                      const float* bias, void* stream);
+int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const float* w_packed, const float* bias,
+                     void* stream);
+/* qkv (B*T, 3*H*64) [q|k|v] with q pre-scaled -> ctx (B*T, H*64).  impl 0 = tcgen05, 1 = SIMT. */
+int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int heads, int is_bf16, int impl,
+                   void* stream);
+/* GraphPool (aasist_modules.py:306-338) on h (B,n,D): out (B,k,D), idx (B,k) descending score. */
+int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
+                    int32_t* idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTDF_H_ */

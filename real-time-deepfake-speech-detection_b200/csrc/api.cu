@@ -1,0 +1,147 @@
+// C-ABI wrappers around single kernels (used by the per-kernel parity tests and by bench.py's
+// roofline measurements).  Lifecycle / forward entry points live in model.cu.
+#include "../../include/rtdf.h"
+#include "aasist.cuh"
+#include "attention.cuh"
+#include "frontend.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+using namespace rtdf;
+
+extern "C" {
+
+int rtdf_preemph(const float* x, float* y, int batch, int n, float coef, void* stream) {
+  return preemph(static_cast<cudaStream_t>(stream), x, y, batch, n, coef);
+}
+
+int rtdf_wave_layernorm(const float* x, float* y, int batch, int n, float eps, void* stream) {
+  return wave_layernorm(static_cast<cudaStream_t>(stream), x, y, batch, n, eps);
+}
+
+int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w, const float* bias, const float* gamma,
+                       const float* beta, float eps, float* out_f32, void* out_bf16, void* stream) {
+  return conv0_ln_gelu(static_cast<cudaStream_t>(stream), wav, batch, n, w, bias, gamma, beta, eps, out_f32,
+                       static_cast<bf16*>(out_bf16));
+}
+
+int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
+                        const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (in_is_bf16)
+    return layernorm_rows_bf16(s, static_cast<const bf16*>(in), rows, cols, gamma, beta, eps, act, out_f32,
+                               static_cast<bf16*>(out_bf16));
+  return layernorm_rows_f32(s, static_cast<const float*>(in), rows, cols, gamma, beta, eps, act, out_f32,
+                            static_cast<bf16*>(out_bf16));
+}
+
+static TcEpilogue make_epi(const float* bias, int act, float scale, const float* resid, float* out_f32, void* out_bf16,
+                           int N) {
+  TcEpilogue e;
+  e.bias = bias;
+  e.act = act;
+  e.scale = scale;
+  e.resid = resid;
+  e.ldr = N;
+  e.out_f32 = out_f32;
+  e.ld_f32 = N;
+  e.out_bf16 = static_cast<bf16*>(out_bf16);
+  e.ld_bf16 = N;
+  return e;
+}
+
+int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const float* bias, int act, float scale,
+                   const float* resid, float* out_f32, void* out_bf16, int variant, void* stream) {
+  RTDF_REQUIRE(out_f32 || out_bf16, "rtdf_gemm_bf16: no output");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(A);
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant,
+                 make_epi(bias, act, scale, resid, out_f32, out_bf16, N));
+}
+
+int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const float* bias, int act, float scale,
+                  const float* resid, float* out_f32, void* stream) {
+  RTDF_REQUIRE(out_f32, "rtdf_gemm_f32: no output");
+  SimtOperandA a;
+  a.ptr = A;
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  return simt_gemm_f32(static_cast<cudaStream_t>(stream), a, W, N, K, make_epi(bias, act, scale, resid, out_f32, nullptr, N));
+}
+
+int rtdf_conv1d_ln_gelu_bf16(const void* x, int batch, int l_in, int k, int stride, const void* w_packed,
+                             const float* bias, const float* gamma, const float* beta, float eps, void* y,
+                             int variant, void* stream) {
+  RTDF_REQUIRE(x && w_packed && y && l_in >= k && k >= 1 && stride >= 1, "rtdf_conv1d_ln_gelu_bf16: bad arguments");
+  const int l_out = (l_in - k) / stride + 1;
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(x);
+  a.k_extent = (long long)k * 512;
+  a.rows_per_batch = l_out;
+  a.batches = batch;
+  a.row_stride = (long long)stride * 512;
+  a.batch_stride = (long long)l_in * 512;
+  TcEpilogue e;
+  e.bias = bias;
+  e.act = ACT_GELU;
+  e.ln_gamma = gamma;
+  e.ln_beta = beta;
+  e.ln_eps = eps;
+  e.out_bf16 = static_cast<bf16*>(y);
+  e.ld_bf16 = 512;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(w_packed), 512, k * 512, TC_PLAIN,
+                 variant, e);
+}
+
+int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames, const void* w_packed,
+                      const float* bias, void* stream) {
+  RTDF_REQUIRE(x_f32 && x_bf16 && w_packed && bias, "rtdf_posconv_bf16: bad arguments");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(x_bf16);
+  a.k_extent = 1024;
+  a.rows_per_batch = n_frames;
+  a.batches = batch;
+  a.row_stride = 1024;
+  a.batch_stride = (long long)n_frames * 1024;
+  TcEpilogue e;
+  e.bias = bias;
+  e.act = ACT_GELU;
+  e.resid = x_f32;
+  e.ldr = 1024;
+  e.out_f32 = x_f32;
+  e.ld_f32 = 1024;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(w_packed), 1024, 8192, TC_POSCONV, 64, e);
+}
+
+int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const float* w_packed, const float* bias,
+                     void* stream) {
+  return posconv_f32(static_cast<cudaStream_t>(stream), x, x_in, batch, n_frames, w_packed, bias);
+}
+
+int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int heads, int is_bf16, int impl,
+                   void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_bf16) {
+    if (impl == 0) return attention_tc(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
+    return attention_simt_bf16(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
+  }
+  RTDF_REQUIRE(impl == 1, "rtdf_attention: the tcgen05 kernel takes bf16 inputs");
+  return attention_simt_f32(s, static_cast<const float*>(qkv), static_cast<float*>(ctx_out), batch, n_frames, heads);
+}
+
+int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
+                    int32_t* idx, void* stream) {
+  GraphView g;
+  g.ptr = h;
+  g.n = n;
+  g.batch_stride = (long long)n * d;
+  return aasist_graph_pool(static_cast<cudaStream_t>(stream), d, g, batch, w, b, k, out, idx);
+}
+
+}  // extern "C"

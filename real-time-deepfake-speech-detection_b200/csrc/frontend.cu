@@ -1,0 +1,436 @@
+// Bandwidth-bound front-end kernels: coalesced, vectorised, warp-shuffle reductions.
+#include "frontend.cuh"
+
+namespace rtdf {
+
+// ------------------------------------------------------------------------------------------------
+// pre-emphasis (reference data/preprocess.py:22-27)
+// ------------------------------------------------------------------------------------------------
+__global__ void preemph_kernel(const float* __restrict__ x, float* __restrict__ y, int N, float coef) {
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * N;
+  float* yb = y + (long long)b * N;
+  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t0 >= N) return;
+  if ((N & 3) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + t0);
+    const float prev = t0 == 0 ? v.y : xb[t0 - 1];  // reflect: x[-1] := x[1]
+    float4 o;
+    o.x = v.x - coef * prev;
+    o.y = v.y - coef * v.x;
+    o.z = v.z - coef * v.y;
+    o.w = v.w - coef * v.z;
+    *reinterpret_cast<float4*>(yb + t0) = o;
+  } else {
+    for (int t = t0; t < min(t0 + 4, N); ++t) {
+      const float prev = t == 0 ? xb[N > 1 ? 1 : 0] : xb[t - 1];
+      yb[t] = xb[t] - coef * prev;
+    }
+  }
+}
+
+int preemph(cudaStream_t s, const float* x, float* y, int B, int N, float coef) {
+  RTDF_REQUIRE(x && y && B > 0 && N > 1, "preemph: bad arguments");
+  RTDF_REQUIRE(x != y, "preemph: in-place operation is not supported");
+  dim3 grid(ceil_div(ceil_div(N, 4), 256), B);
+  preemph_kernel<<<grid, 256, 0, s>>>(x, y, N, coef);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-utterance waveform layer norm (zero mean / unit variance over time); block per utterance
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) wave_ln_kernel(const float* __restrict__ x, float* __restrict__ y, int N, float eps) {
+  __shared__ float red[32];
+  __shared__ float stat[2];
+  const float* xb = x + (long long)blockIdx.x * N;
+  float* yb = y + (long long)blockIdx.x * N;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += xb[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) stat[0] = t / N;
+  }
+  __syncthreads();
+  const float mean = stat[0];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float d = xb[i] - mean;
+    q += d * d;
+  }
+  q = warp_sum(q);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) stat[1] = rsqrtf(t / N + eps);
+  }
+  __syncthreads();
+  const float rstd = stat[1];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) yb[i] = (xb[i] - mean) * rstd;
+}
+
+int wave_layernorm(cudaStream_t s, const float* x, float* y, int B, int N, float eps) {
+  RTDF_REQUIRE(x && y && B > 0 && N > 0, "wave_layernorm: bad arguments");
+  wave_ln_kernel<<<B, 1024, 0, s>>>(x, y, N, eps);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv-0 (C_in = 1, k = 10, stride 5) + bias + LayerNorm(512) + GELU, channels-last output.
+// One warp produces 4 consecutive frames; lane owns channels {j*128 + lane*4 + e}.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__device__ __forceinline__ void store4(TOut* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
+             const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+             float eps, TOut* __restrict__ out) {
+  __shared__ __align__(16) float sw[13][512];  // 10 taps | bias | gamma | beta
+  for (int i = threadIdx.x; i < 10 * 512; i += 256) sw[0][i] = w_t[i];
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    sw[10][i] = bias ? bias[i] : 0.f;
+    sw[11][i] = gamma[i];
+    sw[12][i] = beta[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int t0 = (blockIdx.x * 8 + warp) * 4;
+  if (t0 >= L1) return;
+  const float* xb = wav + (long long)b * N;
+  // 4 frames need samples [5*t0, 5*t0 + 25)
+  float xv = 0.f;
+  {
+    const int i = 5 * t0 + lane;
+    if (lane < 25 && i < N) xv = xb[i];
+  }
+  float acc[4][16];
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[f][c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    float4 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&sw[k][j * 128 + lane * 4]);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const float x = __shfl_sync(0xffffffffu, xv, 5 * f + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[f][j * 4 + 0] = fmaf(x, w[j].x, acc[f][j * 4 + 0]);
+        acc[f][j * 4 + 1] = fmaf(x, w[j].y, acc[f][j * 4 + 1]);
+        acc[f][j * 4 + 2] = fmaf(x, w[j].z, acc[f][j * 4 + 2]);
+        acc[f][j * 4 + 3] = fmaf(x, w[j].w, acc[f][j * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[f][j * 4 + e] += sw[10][j * 128 + lane * 4 + e];
+        s += acc[f][j * 4 + e];
+      }
+    const float mean = warp_sum(s) * (1.0f / 512.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float d = acc[f][c] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + eps);
+    const int t = t0 + f;
+    if (t < L1) {
+      TOut* o = out + ((long long)b * L1 + t) * 512;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = j * 128 + lane * 4 + e;
+          r[e] = gelu_erf((acc[f][j * 4 + e] - mean) * rstd * sw[11][c] + sw[12][c]);
+        }
+        store4<TOut>(o + j * 128 + lane * 4, r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+}
+
+int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w_t, const float* bias,
+                  const float* gamma, const float* beta, float eps, float* out_f32, bf16* out_bf16) {
+  RTDF_REQUIRE(wav && w_t && gamma && beta && N >= 10 && B > 0 && B <= 65535, "conv0: bad arguments");
+  RTDF_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "conv0: exactly one output must be given");
+  const int L1 = (N - 10) / 5 + 1;
+  dim3 grid(ceil_div(L1, 32), B);
+  if (out_f32)
+    conv0_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_f32);
+  else
+    conv0_kernel<bf16><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm.  Fast path: C % 128 == 0 and C <= 1024, one warp per row, row cached in registers
+// (single global read), two-pass statistics.  Generic path: any C, three strided passes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const TIn* __restrict__ in, long long rows, int C, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float eps, int act, float* __restrict__ out_f32,
+               bf16* __restrict__ out_bf16) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int groups = C >> 7;
+  const TIn* p = in + row * C;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < groups) {
+      v[j] = load4(p + j * 128 + lane * 4);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < groups) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < groups) {
+      const int c0 = j * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
+      const float a = apply_act((v[j].x - mean) * rstd * g.x + bt.x, act);
+      const float b = apply_act((v[j].y - mean) * rstd * g.y + bt.y, act);
+      const float c = apply_act((v[j].z - mean) * rstd * g.z + bt.z, act);
+      const float d = apply_act((v[j].w - mean) * rstd * g.w + bt.w, act);
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c0) = make_float4(a, b, c, d);
+      if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+    }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+ln_rows_generic_kernel(const TIn* __restrict__ in, long long rows, int C, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, int act, float* __restrict__ out_f32,
+                       bf16* __restrict__ out_bf16) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TIn* p = in + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += to_f32(p[c]);
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = to_f32(p[c]) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    const float y = apply_act((to_f32(p[c]) - mean) * rstd * gamma[c] + beta[c], act);
+    if (out_f32) out_f32[row * C + c] = y;
+    if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(y);
+  }
+}
+
+template <typename TIn>
+static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const float* gamma, const float* beta,
+                     float eps, int act, float* out_f32, bf16* out_bf16) {
+  RTDF_REQUIRE(in && gamma && beta && rows > 0 && C > 0 && (out_f32 || out_bf16), "layernorm_rows: bad arguments");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if ((C & 127) == 0 && C <= 1024)
+    ln_rows_kernel<TIn><<<grid, 256, 0, s>>>(in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+  else
+    ln_rows_generic_kernel<TIn><<<grid, 256, 0, s>>>(in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+int layernorm_rows_f32(cudaStream_t s, const float* in, long long rows, int C, const float* gamma, const float* beta,
+                       float eps, int act, float* out_f32, bf16* out_bf16) {
+  return ln_launch<float>(s, in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+}
+int layernorm_rows_bf16(cudaStream_t s, const bf16* in, long long rows, int C, const float* gamma, const float* beta,
+                        float eps, int act, float* out_f32, bf16* out_bf16) {
+  return ln_launch<bf16>(s, in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 grouped positional conv (verification mode): one warp per output element, lanes split K = 8192.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+posconv_f32_kernel(float* __restrict__ x, const float* __restrict__ xin, int B, int T,
+                   const float* __restrict__ w, const float* __restrict__ bias) {
+  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)B * T * 1024;
+  if (gw >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int co = (int)(gw % 1024);
+  const int t = (int)((gw / 1024) % T);
+  const int b = (int)(gw / (1024LL * T));
+  const int g = co >> 6;
+  const float* wr = w + (long long)co * 8192;
+  const float* xb = xin + (long long)b * T * 1024 + g * 64;
+  float acc = 0.f;
+  for (int k = 0; k < 128; ++k) {
+    const int tt = t + k - 64;
+    if (tt < 0 || tt >= T) continue;  // warp-uniform
+    const float* xr = xb + (long long)tt * 1024;
+    acc = fmaf(xr[lane], wr[k * 64 + lane], acc);
+    acc = fmaf(xr[lane + 32], wr[k * 64 + lane + 32], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) x[gw] += gelu_erf(acc + bias[co]);
+}
+
+int posconv_f32(cudaStream_t s, float* x, const float* xin, int B, int T, const float* w_packed, const float* bias) {
+  RTDF_REQUIRE(x && xin && x != xin && w_packed && bias, "posconv_f32: bad arguments");
+  const long long total = (long long)B * T * 1024;
+  posconv_f32_kernel<<<(unsigned)((total + 7) / 8), 256, 0, s>>>(x, xin, B, T, w_packed, bias);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing helpers (run once at finalize)
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+int cast_f32_to_bf16(cudaStream_t s, const float* in, bf16* out, long long n) {
+  cast_kernel<<<(unsigned)min((n + 255) / 256, (long long)kNumSMs * 16), 256, 0, s>>>(in, out, n);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+__global__ void scale_kernel(float* w, long long n, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    w[i] *= scale;
+}
+int scale_rows_f32(cudaStream_t s, float* w, long long rows, long long cols, float scale) {
+  const long long n = rows * cols;
+  scale_kernel<<<(unsigned)min((n + 255) / 256, (long long)kNumSMs * 16), 256, 0, s>>>(w, n, scale);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+__global__ void permute_conv_kernel(const float* __restrict__ in, float* __restrict__ out, int co, int ci, int k) {
+  const long long n = (long long)co * ci * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ci);
+    const int kk = (int)((i / ci) % k);
+    const int o = (int)(i / ((long long)ci * k));
+    out[i] = in[((long long)o * ci + c) * k + kk];
+  }
+}
+int permute_conv_weight(cudaStream_t s, const float* in, float* out, int co, int ci, int k) {
+  const long long n = (long long)co * ci * k;
+  permute_conv_kernel<<<(unsigned)min((n + 255) / 256, (long long)kNumSMs * 16), 256, 0, s>>>(in, out, co, ci, k);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// one block per tap k: norm over (co, ci) of v[:, :, k], then scaled, permuted write
+__global__ void __launch_bounds__(1024)
+posconv_fold_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ out, int co, int ci, int k) {
+  __shared__ float red[32];
+  __shared__ float scale_s;
+  const int kk = blockIdx.x;
+  const long long n = (long long)co * ci;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = v[i * k + kk];
+    s += x * x;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = red[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) scale_s = g[kk] / sqrtf(t);
+  }
+  __syncthreads();
+  const float sc = scale_s;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (int)(i % ci);
+    const int o = (int)(i / ci);
+    out[((long long)o * k + kk) * ci + c] = v[i * k + kk] * sc;
+  }
+}
+int posconv_fold_weight(cudaStream_t s, const float* v, const float* g, float* out, int co, int ci, int k) {
+  posconv_fold_kernel<<<k, 1024, 0, s>>>(v, g, out, co, ci, k);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int r, int c) {
+  const int n = r * c;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int rr = i / c, cc = i % c;
+    out[cc * r + rr] = in[i];
+  }
+}
+int transpose_f32(cudaStream_t s, const float* in, float* out, int r, int c) {
+  transpose_kernel<<<ceil_div(r * c, 256), 256, 0, s>>>(in, out, r, c);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+__global__ void bn_fold_kernel(const float* w, const float* b, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sc = w[i] / sqrtf(var[i] + eps);
+  scale[i] = sc;
+  shift[i] = b[i] - mean[i] * sc;
+}
+int bn_fold(cudaStream_t s, const float* w, const float* b, const float* mean, const float* var, float eps,
+            float* scale, float* shift, int n) {
+  bn_fold_kernel<<<ceil_div(n, 128), 128, 0, s>>>(w, b, mean, var, eps, scale, shift, n);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+}  // namespace rtdf

@@ -1,0 +1,45 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] * W[N,K]^T), bf16 in, fp32 accumulate.
+#pragma once
+#include "common.cuh"
+
+namespace rtdf {
+
+struct TcEpilogue {
+  const float* bias = nullptr;     // [N]
+  int act = ACT_NONE;              // applied to acc + bias
+  float scale = 1.0f;              // multiplies the activated value
+  const float* resid = nullptr;    // fp32 [rows, ldr], added last (may alias out_f32)
+  long long ldr = 0;
+  float* out_f32 = nullptr;        // optional fp32 output
+  long long ld_f32 = 0;
+  bf16* out_bf16 = nullptr;        // optional bf16 output
+  long long ld_bf16 = 0;
+  // row-LayerNorm fused epilogue (only for the N == 512 full-row variant): y = act(LN(acc + bias))
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 1e-5f;
+};
+
+// A operand as a (k, row, batch) strided view of bf16 memory.  Plain GEMM: batches = 1.
+// Implicit-GEMM 1-D conv on channels-last activations: row t of batch b is the contiguous slab
+// x[b, stride*t : stride*t + k, 0:C]  =>  k_extent = k*C, row_stride = stride*C, batch_stride = L_in*C.
+struct TcOperandA {
+  const bf16* ptr = nullptr;
+  long long k_extent = 0;
+  long long rows_per_batch = 0;
+  long long batches = 1;
+  long long row_stride = 0;    // elements
+  long long batch_stride = 0;  // elements
+};
+
+enum TcMode {
+  TC_PLAIN = 0,    // A tile (m0, kb*BK)
+  TC_POSCONV = 1,  // grouped k=128 conv as shifted-row GEMM: A tile (m0 + kb - 64, g*64), W tile (g*64, kb*64)
+};
+
+// variant: 64, 128, 256 -> plain tiles 128 x variant;  512 -> full-row tile with fused LayerNorm (BK 64);
+//          513 -> same with BK 32 / 64-byte swizzle (deeper pipeline)
+int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, int mode, int variant,
+            const TcEpilogue& epi);
+
+}  // namespace rtdf

@@ -1,0 +1,112 @@
+// Model context: weight store, packed weights, workspace plan, forward orchestration.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rtdf.h"
+#include "aasist.cuh"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace rtdf {
+
+struct Raw {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  long long numel = 0;
+};
+
+struct Lin {          // y = W x + b, W: [n][k]
+  const float* w = nullptr;
+  const bf16* wb = nullptr;
+  const float* b = nullptr;
+  int n = 0, k = 0;
+};
+
+struct Norm {         // LayerNorm affine or folded BatchNorm scale/shift
+  const float* g = nullptr;
+  const float* b = nullptr;
+};
+
+struct FeConv {
+  Lin lin;            // packed [512][k*512] (tap-major) ; conv-0: lin.w = [10][512]
+  Norm ln;
+  int k = 0, stride = 0;
+};
+
+struct XlsrLayer {
+  Lin qkv, out, fc1, fc2;
+  Norm ln1, ln2;
+};
+
+struct ResBlockW {
+  const float* conv1_w = nullptr; const float* conv1_b = nullptr;
+  Norm bn2;
+  const float* conv2_w = nullptr; const float* conv2_b = nullptr;
+  const float* ds_w = nullptr; const float* ds_b = nullptr;
+  int ci = 0, co = 0;
+};
+
+struct HsGalW {
+  const float* t1_wt = nullptr; const float* t1_b = nullptr;
+  const float* t2_wt = nullptr; const float* t2_b = nullptr;
+  GatRowWeights rows, master;
+  int d = 0, dout = 0;
+};
+
+struct PoolW { const float* w = nullptr; const float* b = nullptr; };
+
+struct AasistW {
+  Lin LL;
+  float first_bn_s = 1.f, first_bn_t = 0.f;
+  ResBlockW blocks[6];
+  Norm first_bn1;
+  const float* att_w1t = nullptr; const float* att_b1 = nullptr; Norm att_bn;
+  const float* att_w2t = nullptr; const float* att_b2 = nullptr;
+  const float* pos_S = nullptr; const float* master1 = nullptr; const float* master2 = nullptr;
+  GatRowWeights gat_S, gat_T;
+  HsGalW st11, st12, st21, st22;
+  PoolW pool_S, pool_T, pool_hS1, pool_hT1, pool_hS2, pool_hT2;
+  const float* out_w = nullptr; const float* out_b = nullptr;
+};
+
+struct ConformerBlockW {
+  Norm ff1_ln, ff2_ln, attn_ln, conv_ln, post_ln;
+  Lin ff1_a, ff1_b, ff2_a, ff2_b;     // 144->576, 576->144
+  Lin qkv;                            // fused [to_q ; to_kv] (432 x 144), no bias
+  Lin attn_out;
+  const float* rel_pos = nullptr;     // [1025][dim_head]
+  Lin pw1;                            // pointwise 144 -> 576 (GLU halves)
+  const float* dw_w = nullptr;        // [288][k]
+  const float* dw_b = nullptr;
+  Norm dw_bn;                         // folded BatchNorm1d(288)
+  Lin pw2;                            // 288 -> 144
+};
+
+struct ConformerW {
+  Lin LL;
+  float first_bn_s = 1.f, first_bn_t = 0.f;
+  const float* class_token = nullptr;
+  std::vector<ConformerBlockW> blocks;
+  Lin fc5;
+};
+
+}  // namespace rtdf
+
+struct rtdf_ctx {
+  int device = 0;
+  rtdf_model_desc d{};
+  bool finalized = false;
+  std::map<std::string, rtdf::Raw> raw;
+  std::vector<void*> owned;
+  // XLS-R
+  rtdf::FeConv fe[7];
+  rtdf::Norm fp_ln;
+  rtdf::Lin proj;
+  rtdf::Lin pos;      // packed [1024][8192]
+  std::vector<rtdf::XlsrLayer> layers;
+  rtdf::Norm enc_ln;
+  rtdf::AasistW aasist;
+  rtdf::ConformerW conf;
+};

@@ -1,0 +1,117 @@
+"""Block- and end-to-end parity of the CUDA path against the CPU oracle and the committed golden
+vectors (which were produced by the reference's own model files, see oracle/check_against_reference.py).
+
+Tolerances (BASELINE.json north_star): max |logit diff| <= 1e-4 in fp32 mode, <= 1e-2 in bf16 mode;
+GraphPool node selection bit-exact when fed identical fp32 inputs (rows with distinct scores)."""
+import os
+
+import numpy as np
+import torch
+
+from tests.util import ROOT, build_pair
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _waves(B, N, seed=2021):
+    from oracle.models_ref import synth_waveforms
+    return synth_waveforms(B, N, seed=seed)
+
+
+def check_backend_block(precision="fp32", B=3, N=16000):
+    """Feed the oracle's own XLS-R features to the CUDA back-end only."""
+    ora, prod = build_pair("XLSR_AASIST", precision)
+    x = _waves(B, N)
+    taps = {}
+    with torch.no_grad():
+        ref = ora(x, taps)
+    eng = prod.engine()
+    logits, t = eng.backend(taps["feats"].cuda(), want_taps=True)
+    d = float((logits.cpu() - ref).abs().max())
+    same_S = bool((t["idx_S"].cpu().long() == taps["idx_S"]).all())
+    same_T = bool((t["idx_T"].cpu().long() == taps["idx_T"]).all())
+    res = {"max_dlogit": d, "idx_S_equal": same_S, "idx_T_equal": same_T, "ref0": ref[0].tolist()}
+    if precision == "fp32":
+        assert same_S and same_T, res       # identical fp32 input -> identical top-k selection and order
+    assert d <= TOL[precision], res
+    return res
+
+
+def check_frontend_block(precision="fp32", B=2, N=16000, kind="XLSR_AASIST", **kw):
+    ora, prod = build_pair(kind, precision, **kw)
+    x = _waves(B, N)
+    with torch.no_grad():
+        ref = ora.ssl_model.extract_feat(x)
+    got = prod.ssl_model.extract_feat(x.cuda()).cpu()
+    d = float((got - ref).abs().max())
+    rel = d / float(ref.abs().max())
+    res = {"max_abs": d, "rel_to_max": rel, "ref_absmean": float(ref.abs().mean())}
+    assert d <= (2e-4 if precision == "fp32" else 0.08), res   # LayerNorm-ed features are O(1); bf16 through 24 layers
+    return res
+
+
+def check_e2e(kind="XLSR_AASIST", precision="fp32", B=2, N=16000, **kw):
+    ora, prod = build_pair(kind, precision, **kw)
+    x = _waves(B, N)
+    with torch.no_grad():
+        ref = ora(x)
+    got = prod(x.cuda()).cpu()
+    d = float((got - ref).abs().max())
+    res = {"max_dlogit": d, "ref0": ref[0].tolist(), "got0": got[0].tolist()}
+    assert got.shape == (B, 2) and got.dtype == torch.float32
+    assert d <= TOL[precision], res
+    return res
+
+
+def check_golden(name, precision="fp32"):
+    """CUDA path vs logits produced by the reference's own files (committed fixture)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+    kw = eval(str(g["kwargs"]))
+    kind = str(g["kind"])
+    if kind == "MyModel":
+        kw["fixed_call"] = True
+    ora, prod = build_pair(kind, precision, seed=int(g["seed"]), **kw)
+    x = _waves(int(g["B"]), int(g["N"]), seed=int(g["wave_seed"]))
+    if "idx_S" in g.files:
+        got, taps = prod(x.cuda(), return_taps=True)
+    else:
+        got, taps = prod(x.cuda()), None
+    ref = torch.from_numpy(g["logits"])
+    d = float((got.cpu() - ref).abs().max())
+    res = {"max_dlogit_vs_reference": d}
+    if taps is not None:
+        fh = torch.from_numpy(g["feats_head"])
+        res["feats_head_maxdiff"] = float((taps["feats"][:, :4, :16].cpu() - fh).abs().max())
+        res["idx_S_equal"] = bool((taps["idx_S"].cpu().long() == torch.from_numpy(g["idx_S"])).all())
+        res["idx_T_equal"] = bool((taps["idx_T"].cpu().long() == torch.from_numpy(g["idx_T"])).all())
+    assert d <= TOL[precision], res
+    return res
+
+
+def check_ragged_and_quirks(precision="fp32"):
+    """Ragged last batch (B=1), (B,N,1) input, odd T, pre-emphasis flag, determinism."""
+    ora, prod = build_pair("XLSR_AASIST", precision)
+    from oracle.models_ref import pre_emphasis
+    res = {}
+    for B, N in ((1, 16000), (3, 16400)):
+        x = _waves(B, N, seed=77)
+        with torch.no_grad():
+            ref = ora(x)
+        got = prod(x.cuda().unsqueeze(-1)).cpu()
+        res[f"B{B}_N{N}"] = float((got - ref).abs().max())
+        assert res[f"B{B}_N{N}"] <= TOL[precision], res
+    x = _waves(2, 16000, seed=78)
+    with torch.no_grad():
+        ref = ora(pre_emphasis(x))
+    eng = prod.engine()
+    got = eng.forward(x.cuda(), preemph=True, coef=0.97).cpu()
+    res["preemph"] = float((got - ref).abs().max())
+    assert res["preemph"] <= TOL[precision], res
+    again = eng.forward(x.cuda(), preemph=True, coef=0.97).cpu()
+    assert torch.equal(got, again), "forward is not deterministic"
+    # batch composition must not change per-utterance results (multi-GPU sharding relies on it)
+    solo = torch.cat([eng.forward(x[i:i + 1].cuda(), preemph=True).cpu() for i in range(2)])
+    res["batch_invariance"] = float((solo - got).abs().max())
+    assert res["batch_invariance"] == 0.0, res
+    return res

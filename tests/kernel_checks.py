@@ -1,0 +1,253 @@
+"""Per-kernel parity checks of the CUDA path (through the C-ABI) against plain fp32 PyTorch
+references of the same op.  Each check returns a dict of measured errors and raises
+AssertionError with the numbers when a tolerance (written next to each assert) is exceeded.
+Used by tests/test_kernels_gpu.py and tools/gpu_diag.py."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from tests.util import P, call, gemm_bf16, gemm_f32, stream
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+def check_preemph():
+    from oracle.models_ref import pre_emphasis, synth_waveforms
+    out = {}
+    for B, N in ((3, 4000), (2, 64600), (1, 4001)):
+        x = synth_waveforms(B, N, seed=5)
+        ref = pre_emphasis(x).reshape(B, N)
+        xd = x.to(DEV)
+        y = torch.empty_like(xd)
+        call("rtdf_preemph", P(xd), P(y), B, N, 0.97, stream())
+        d = float((y.cpu() - ref).abs().max())
+        out[f"{B}x{N}"] = d
+        assert d <= 1e-6, out      # fp32, FMA contraction only
+    return out
+
+
+def check_wave_layernorm():
+    x = torch.randn(3, 16000) * 0.3 + 0.1
+    xd = x.to(DEV)
+    y = torch.empty_like(xd)
+    call("rtdf_wave_layernorm", P(xd), P(y), 3, 16000, 1e-5, stream())
+    ref = F.layer_norm(x, (16000,))
+    d = float((y.cpu() - ref).abs().max())
+    assert d <= 2e-5, d
+    return {"max_abs": d}
+
+
+def check_layernorm():
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    for rows, C in ((37, 1024), (130, 512), (201, 144), (9, 128)):
+        x = torch.randn(rows, C, generator=g) * 2 + 0.5
+        gamma = 1 + 0.1 * torch.randn(C, generator=g)
+        beta = 0.1 * torch.randn(C, generator=g)
+        ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+        for in_bf16 in (0, 1):
+            xin = x.to(DEV).to(torch.bfloat16) if in_bf16 else x.to(DEV)
+            r = F.layer_norm(xin.float().cpu(), (C,), gamma, beta, 1e-5) if in_bf16 else ref
+            o32 = torch.empty(rows, C, dtype=torch.float32, device=DEV)
+            o16 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
+            call("rtdf_layernorm_rows", P(xin), in_bf16, rows, C, P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5, 0, P(o32),
+                 P(o16), stream())
+            d32 = float((o32.cpu() - r).abs().max())
+            d16 = float((o16.float().cpu() - r).abs().max())
+            out[f"{rows}x{C}_bf16in{in_bf16}"] = (d32, d16)
+            assert d32 <= 2e-5, out      # fp32 statistics
+            assert d16 <= 0.04, out      # bf16 output rounding of O(4) values
+        # fused GELU
+        o32 = torch.empty(rows, C, dtype=torch.float32, device=DEV)
+        call("rtdf_layernorm_rows", P(x.to(DEV)), 0, rows, C, P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5, 1, P(o32), None, stream())
+        d = float((o32.cpu() - F.gelu(ref)).abs().max())
+        assert d <= 2e-5, d
+    return out
+
+
+def check_conv0():
+    g = torch.Generator().manual_seed(1)
+    out = {}
+    for B, N in ((2, 16000), (1, 4003)):
+        wav = torch.randn(B, N, generator=g) * 0.1
+        w = torch.randn(512, 1, 10, generator=g) * 0.4
+        b = torch.randn(512, generator=g) * 0.1
+        gamma = 1 + 0.1 * torch.randn(512, generator=g)
+        beta = 0.1 * torch.randn(512, generator=g)
+        y = F.conv1d(wav.unsqueeze(1), w, b, stride=5)            # (B,512,L)
+        ref = F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))   # (B,L,512)
+        L = ref.shape[1]
+        wt = w[:, 0, :].t().contiguous().to(DEV)
+        o32 = torch.empty(B, L, 512, dtype=torch.float32, device=DEV)
+        call("rtdf_conv0_ln_gelu", P(wav.to(DEV)), B, N, P(wt), P(b.to(DEV)), P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5,
+             P(o32), None, stream())
+        o16 = torch.empty(B, L, 512, dtype=torch.bfloat16, device=DEV)
+        call("rtdf_conv0_ln_gelu", P(wav.to(DEV)), B, N, P(wt), P(b.to(DEV)), P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5,
+             None, P(o16), stream())
+        d32 = float((o32.cpu() - ref).abs().max())
+        d16 = float((o16.float().cpu() - ref).abs().max())
+        out[f"{B}x{N}"] = (d32, d16)
+        assert d32 <= 5e-5, out
+        assert d16 <= 0.03, out
+    return out
+
+
+def check_gemm_f32():
+    g = torch.Generator().manual_seed(2)
+    out = {}
+    for M, N, K in ((70, 130, 96), (257, 64, 1024), (33, 2, 144)):
+        A = torch.randn(M, K, generator=g)
+        W = torch.randn(N, K, generator=g) / math.sqrt(K)
+        b = torch.randn(N, generator=g)
+        R = torch.randn(M, N, generator=g)
+        ref = F.gelu(A @ W.t() + b) * 0.5 + R
+        o = gemm_f32(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=0.5, resid=R.to(DEV))
+        d = float((o.cpu() - ref).abs().max())
+        out[f"{M}x{N}x{K}"] = d
+        assert d <= 2e-5, out
+    return out
+
+
+def check_gemm_bf16(variants=(64, 128, 256)):
+    g = torch.Generator().manual_seed(3)
+    out = {}
+    shapes = ((128, 256, 64), (300, 256, 128), (1000, 3072, 1024), (200, 144, 144), (131, 576, 144), (77, 1024, 4096),
+              (402, 128, 1024))
+    for M, N, K in shapes:
+        A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, generator=g)
+        R = torch.randn(M, N, generator=g)
+        base = A.float() @ W.float().t()
+        for v in variants:
+            o = gemm_bf16(A.to(DEV), W.to(DEV), variant=v)
+            d0 = float((o.cpu() - base).abs().max())
+            o32, o16 = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=0.5, resid=R.to(DEV), out="both", variant=v)
+            ref = F.gelu(base + b) * 0.5 + R
+            d1 = float((o32.cpu() - ref).abs().max())
+            d2 = float((o16.float().cpu() - ref).abs().max())
+            out[f"{M}x{N}x{K}_v{v}"] = (d0, d1, d2)
+            assert d0 <= 2e-3, out     # fp32 accumulation of exact bf16 products, different summation order
+            assert d1 <= 2e-3, out
+            assert d2 <= 0.05, out     # bf16 output rounding
+    return out
+
+
+def _conv_ref(x, w, b, gamma, beta, stride):
+    y = F.conv1d(x.transpose(1, 2), w, b, stride=stride)             # (B,512,L)
+    return F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))
+
+
+def check_conv1d_tc(variants=(512, 513)):
+    g = torch.Generator().manual_seed(4)
+    out = {}
+    for B, L, k in ((2, 799, 3), (1, 403, 2), (3, 130, 3)):
+        x = torch.randn(B, L, 512, generator=g).to(torch.bfloat16)
+        w = (torch.randn(512, 512, k, generator=g) / math.sqrt(512 * k)).to(torch.bfloat16)
+        b = torch.randn(512, generator=g) * 0.1
+        gamma = 1 + 0.1 * torch.randn(512, generator=g)
+        beta = 0.1 * torch.randn(512, generator=g)
+        ref = _conv_ref(x.float(), w.float(), b, gamma, beta, 2)
+        Lo = ref.shape[1]
+        wp = w.permute(0, 2, 1).contiguous().to(DEV)               # [co][k][ci]
+        for v in variants:
+            y = torch.zeros(B, Lo, 512, dtype=torch.bfloat16, device=DEV)
+            call("rtdf_conv1d_ln_gelu_bf16", P(x.to(DEV)), B, L, k, 2, P(wp), P(b.to(DEV)), P(gamma.to(DEV)),
+                 P(beta.to(DEV)), 1e-5, P(y), v, stream())
+            d = float((y.float().cpu() - ref).abs().max())
+            out[f"B{B}_L{L}_k{k}_v{v}"] = d
+            assert d <= 0.04, out    # bf16 output rounding of O(4) values
+    return out
+
+
+def _posconv_ref(x, w, bias):
+    B, T, C = x.shape
+    y = F.conv1d(x.transpose(1, 2), w, bias, padding=64, groups=16)[:, :, :T]
+    return x + F.gelu(y).transpose(1, 2)
+
+
+def check_posconv():
+    g = torch.Generator().manual_seed(5)
+    out = {}
+    for B, T in ((2, 199), (1, 49), (2, 130)):
+        x = torch.randn(B, T, 1024, generator=g)
+        w = torch.randn(1024, 64, 128, generator=g) / math.sqrt(64 * 128)
+        bias = torch.randn(1024, generator=g) * 0.1
+        wp = w.permute(0, 2, 1).reshape(1024, 8192).contiguous()    # [co][k*64+ci]
+        ref32 = _posconv_ref(x, w, bias)
+        xo = x.clone().to(DEV)
+        call("rtdf_posconv_f32", P(xo), P(x.to(DEV)), B, T, P(wp.to(DEV)), P(bias.to(DEV)), stream())
+        d32 = float((xo.cpu() - ref32).abs().max())
+        xb = x.to(torch.bfloat16)
+        wb = wp.to(torch.bfloat16)
+        ref16 = x + (_posconv_ref(xb.float(), wb.float().reshape(1024, 128, 64).permute(0, 2, 1), bias) - xb.float())
+        xo2 = x.clone().to(DEV)
+        call("rtdf_posconv_bf16", P(xo2), P(xb.to(DEV)), B, T, P(wb.to(DEV)), P(bias.to(DEV)), stream())
+        d16 = float((xo2.cpu() - ref16).abs().max())
+        out[f"B{B}_T{T}"] = (d32, d16)
+        assert d32 <= 5e-5, out
+        assert d16 <= 2e-3, out
+    return out
+
+
+def _attn_ref(qkv, B, T, H):
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2), dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
+
+
+def check_attention(impls=(0, 1)):
+    g = torch.Generator().manual_seed(6)
+    out = {}
+    for B, T, H in ((2, 199, 16), (1, 49, 16), (2, 201, 4), (1, 128, 2), (1, 256, 2), (3, 17, 1)):
+        qkv = torch.randn(B * T, 3 * H * 64, generator=g)
+        qkv[:, : H * 64] *= 0.25
+        ref32 = _attn_ref(qkv, B, T, H)
+        o = torch.empty(B * T, H * 64, dtype=torch.float32, device=DEV)
+        call("rtdf_attention", P(qkv.to(DEV)), P(o), B, T, H, 0, 1, stream())
+        d = float((o.cpu() - ref32).abs().max())
+        out[f"B{B}_T{T}_H{H}_f32"] = d
+        assert d <= 2e-5, out
+        qb = qkv.to(torch.bfloat16)
+        ref16 = _attn_ref(qb, B, T, H)
+        for impl in impls:
+            o16 = torch.zeros(B * T, H * 64, dtype=torch.bfloat16, device=DEV)
+            call("rtdf_attention", P(qb.to(DEV)), P(o16), B, T, H, 1, impl, stream())
+            d = float((o16.float().cpu() - ref16).abs().max())
+            out[f"B{B}_T{T}_H{H}_bf16_impl{impl}"] = d
+            assert d <= 0.03, out     # bf16 P and bf16 output rounding, |out| <~ 3
+    return out
+
+
+def check_graph_pool():
+    from oracle.aasist_ref import GraphPool
+    out = {}
+    torch.manual_seed(7)
+    for B, n, D in ((4, 42, 64), (3, 67, 64), (2, 33, 32), (5, 21, 32), (2, 1, 32), (2, 16, 32)):
+        gp = GraphPool(0.5, D).eval()
+        h = torch.randn(B, n, D)
+        with torch.no_grad():
+            ref, idx = gp(h, return_idx=True)
+        k = ref.shape[1]
+        o = torch.empty(B, k, D, dtype=torch.float32, device=DEV)
+        io = torch.empty(B, k, dtype=torch.int32, device=DEV)
+        call("rtdf_graph_pool", P(h.to(DEV)), B, n, D, P(gp.proj.weight.detach().to(DEV)), P(gp.proj.bias.detach().to(DEV)),
+             k, P(o), P(io), stream())
+        same = bool((io.cpu().long() == idx).all())
+        d = float((o.cpu() - ref).abs().max())
+        out[f"B{B}_n{n}_D{D}"] = (same, d)
+        assert same, out            # bit-exact node selection and order (distinct scores)
+        assert d <= 1e-6, out
+    # ties: equal scores keep the lower index first (documented tie rule)
+    h = torch.ones(1, 8, 32)
+    o = torch.empty(1, 4, 32, device=DEV)
+    io = torch.empty(1, 4, dtype=torch.int32, device=DEV)
+    w = torch.ones(32)
+    call("rtdf_graph_pool", P(h.to(DEV)), 1, 8, 32, P(w.to(DEV)), P(torch.zeros(1).to(DEV)), 4, P(o), P(io), stream())
+    assert io.cpu().tolist() == [[0, 1, 2, 3]], io
+    return out

@@ -1,0 +1,68 @@
+"""Shared helpers for the tests: package import, C-ABI call wrappers, model construction."""
+import ctypes
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG_NAME = "real-time-deepfake-speech-detection_b200"
+
+
+def pkg(sub=""):
+    return importlib.import_module(PKG_NAME + (("." + sub) if sub else ""))
+
+
+def native():
+    return pkg("rtdf_runtime.native")
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    nat = native()
+    lib = nat.load()
+    nat.check(getattr(lib, name)(*args), name)
+
+
+def gemm_bf16(A, W, bias=None, act=0, scale=1.0, resid=None, out="f32", variant=256):
+    M, K = A.shape
+    N = W.shape[0]
+    o32 = torch.empty(M, N, dtype=torch.float32, device=A.device) if out in ("f32", "both") else None
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=A.device) if out in ("bf16", "both") else None
+    call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, scale, P(resid), P(o32), P(o16), variant, stream())
+    return o32 if out == "f32" else (o16 if out == "bf16" else (o32, o16))
+
+
+def gemm_f32(A, W, bias=None, act=0, scale=1.0, resid=None):
+    M, K = A.shape
+    N = W.shape[0]
+    o = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    call("rtdf_gemm_f32", P(A), P(W), M, N, K, P(bias), act, scale, P(resid), P(o), stream())
+    return o
+
+
+def build_pair(kind, precision, seed=1024, device="cuda", **kwargs):
+    """(oracle model on CPU, product model on `device`) with identical seeded weights."""
+    from oracle import models_ref as O
+    ora = O.build(kind, seed=seed, **kwargs)
+    if kind in ("XLSR_AASIST", "My_XLSR_AASIST"):
+        cls = getattr(pkg("models.xlsr_aasist"), kind)
+        prod = cls("cpu", None, **kwargs)
+    else:
+        mod = pkg("models.conformer_baseline")
+        prod = mod.Model("cpu", None, **kwargs) if kind == "ConformerModel" else mod.MyModel("cpu", None, **kwargs)
+    prod.load_state_dict(ora.state_dict(), strict=True)
+    prod = prod.to(device).eval()
+    prod.rtdf_precision = precision
+    return ora, prod

@@ -120,6 +120,15 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream);
 
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* Total number of kernels this library has launched in the calling process. */
+long long rtdf_launch_count(void);
+/* Bracket a region: every tcgen05 GEMM launch in it is timed with CUDA events on its own stream.
+ * rtdf_profile_end sums duration (ms) and algorithmic FLOPs (2*M*N*K) of the launches of one tile
+ * variant (64|128|256|512|513, or -1 for all). */
+int rtdf_profile_begin(void);
+int rtdf_profile_end(int variant, double* ms_total, double* flops_total, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,6 +135,15 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
   return attention_simt_f32(s, static_cast<const float*>(qkv), static_cast<float*>(ctx_out), batch, n_frames, heads);
 }
 
+long long rtdf_launch_count(void) { return launch_count(); }
+int rtdf_profile_begin(void) {
+  tc_profile_begin();
+  return RTDF_OK;
+}
+int rtdf_profile_end(int variant, double* ms_total, double* flops_total, int* launches) {
+  return tc_profile_end(variant, ms_total, flops_total, launches);
+}
+
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream) {
   GraphView g;

@@ -172,7 +172,8 @@ conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restri
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = j * 128 + lane * 4 + e;
-          r[e] = gelu_erf((acc[f][j * 4 + e] - mean) * rstd * sw[11][c] + sw[12][c]);
+          const float y = (acc[f][j * 4 + e] - mean) * rstd * sw[11][c] + sw[12][c];
+          r[e] = sizeof(TOut) == 2 ? gelu_fast(y) : gelu_erf(y);   // bf16 output: A&S erf (1.5e-7) suffices
         }
         store4<TOut>(o + j * 128 + lane * 4, r[0], r[1], r[2], r[3]);
       }

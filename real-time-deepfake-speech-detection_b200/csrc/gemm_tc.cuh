@@ -42,4 +42,8 @@ enum TcMode {
 int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, int mode, int variant,
             const TcEpilogue& epi);
 
+// per-launch CUDA-event timing of tc_gemm launches (variant: 64|128|256|512|513, or -1 = all)
+void tc_profile_begin();
+int tc_profile_end(int variant, double* ms_total, double* flops_total, int* launches);
+
 }  // namespace rtdf

@@ -15,6 +15,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+long long launch_count() { return g_launches; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

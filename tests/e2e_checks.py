@@ -40,6 +40,7 @@ def check_backend_block(precision="fp32", B=3, N=16000):
 
 def check_frontend_block(precision="fp32", B=2, N=16000, kind="XLSR_AASIST", **kw):
     ora, prod = build_pair(kind, precision, **kw)
+    prod.ssl_model.rtdf_precision = precision
     x = _waves(B, N)
     with torch.no_grad():
         ref = ora.ssl_model.extract_feat(x)

@@ -10,6 +10,18 @@ import torch.nn.functional as F
 from tests.util import P, call, gemm_bf16, gemm_f32, stream
 
 DEV = "cuda"
+_KEEP = []
+
+
+def dev(t):
+    """Copy to the device and keep the tensor alive (a bare P(dev(x)) would free it before the launch)."""
+    d = t.to(DEV)
+    _KEEP.append(d)
+    if len(_KEEP) > 256:
+        torch.cuda.synchronize()
+        del _KEEP[:128]
+    return d
+
 
 
 def _rel(a, b):
@@ -55,7 +67,7 @@ def check_layernorm():
             r = F.layer_norm(xin.float().cpu(), (C,), gamma, beta, 1e-5) if in_bf16 else ref
             o32 = torch.empty(rows, C, dtype=torch.float32, device=DEV)
             o16 = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
-            call("rtdf_layernorm_rows", P(xin), in_bf16, rows, C, P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5, 0, P(o32),
+            call("rtdf_layernorm_rows", P(xin), in_bf16, rows, C, P(dev(gamma)), P(dev(beta)), 1e-5, 0, P(o32),
                  P(o16), stream())
             d32 = float((o32.cpu() - r).abs().max())
             d16 = float((o16.float().cpu() - r).abs().max())
@@ -64,7 +76,7 @@ def check_layernorm():
             assert d16 <= 0.04, out      # bf16 output rounding of O(4) values
         # fused GELU
         o32 = torch.empty(rows, C, dtype=torch.float32, device=DEV)
-        call("rtdf_layernorm_rows", P(x.to(DEV)), 0, rows, C, P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5, 1, P(o32), None, stream())
+        call("rtdf_layernorm_rows", P(dev(x)), 0, rows, C, P(dev(gamma)), P(dev(beta)), 1e-5, 1, P(o32), None, stream())
         d = float((o32.cpu() - F.gelu(ref)).abs().max())
         assert d <= 2e-5, d
     return out
@@ -84,10 +96,10 @@ def check_conv0():
         L = ref.shape[1]
         wt = w[:, 0, :].t().contiguous().to(DEV)
         o32 = torch.empty(B, L, 512, dtype=torch.float32, device=DEV)
-        call("rtdf_conv0_ln_gelu", P(wav.to(DEV)), B, N, P(wt), P(b.to(DEV)), P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5,
+        call("rtdf_conv0_ln_gelu", P(dev(wav)), B, N, P(wt), P(dev(b)), P(dev(gamma)), P(dev(beta)), 1e-5,
              P(o32), None, stream())
         o16 = torch.empty(B, L, 512, dtype=torch.bfloat16, device=DEV)
-        call("rtdf_conv0_ln_gelu", P(wav.to(DEV)), B, N, P(wt), P(b.to(DEV)), P(gamma.to(DEV)), P(beta.to(DEV)), 1e-5,
+        call("rtdf_conv0_ln_gelu", P(dev(wav)), B, N, P(wt), P(dev(b)), P(dev(gamma)), P(dev(beta)), 1e-5,
              None, P(o16), stream())
         d32 = float((o32.cpu() - ref).abs().max())
         d16 = float((o16.float().cpu() - ref).abs().max())
@@ -146,7 +158,7 @@ def _conv_ref(x, w, b, gamma, beta, stride):
 def check_conv1d_tc(variants=(512, 513)):
     g = torch.Generator().manual_seed(4)
     out = {}
-    for B, L, k in ((2, 799, 3), (1, 403, 2), (3, 130, 3)):
+    for B, L, k in ((2, 799, 3), (1, 403, 2), (3, 130, 3), (2, 12799, 3)):
         x = torch.randn(B, L, 512, generator=g).to(torch.bfloat16)
         w = (torch.randn(512, 512, k, generator=g) / math.sqrt(512 * k)).to(torch.bfloat16)
         b = torch.randn(512, generator=g) * 0.1
@@ -157,8 +169,8 @@ def check_conv1d_tc(variants=(512, 513)):
         wp = w.permute(0, 2, 1).contiguous().to(DEV)               # [co][k][ci]
         for v in variants:
             y = torch.zeros(B, Lo, 512, dtype=torch.bfloat16, device=DEV)
-            call("rtdf_conv1d_ln_gelu_bf16", P(x.to(DEV)), B, L, k, 2, P(wp), P(b.to(DEV)), P(gamma.to(DEV)),
-                 P(beta.to(DEV)), 1e-5, P(y), v, stream())
+            call("rtdf_conv1d_ln_gelu_bf16", P(dev(x)), B, L, k, 2, P(wp), P(dev(b)), P(dev(gamma)),
+                 P(dev(beta)), 1e-5, P(y), v, stream())
             d = float((y.float().cpu() - ref).abs().max())
             out[f"B{B}_L{L}_k{k}_v{v}"] = d
             assert d <= 0.04, out    # bf16 output rounding of O(4) values
@@ -181,13 +193,13 @@ def check_posconv():
         wp = w.permute(0, 2, 1).reshape(1024, 8192).contiguous()    # [co][k*64+ci]
         ref32 = _posconv_ref(x, w, bias)
         xo = x.clone().to(DEV)
-        call("rtdf_posconv_f32", P(xo), P(x.to(DEV)), B, T, P(wp.to(DEV)), P(bias.to(DEV)), stream())
+        call("rtdf_posconv_f32", P(xo), P(dev(x)), B, T, P(dev(wp)), P(dev(bias)), stream())
         d32 = float((xo.cpu() - ref32).abs().max())
         xb = x.to(torch.bfloat16)
         wb = wp.to(torch.bfloat16)
         ref16 = x + (_posconv_ref(xb.float(), wb.float().reshape(1024, 128, 64).permute(0, 2, 1), bias) - xb.float())
         xo2 = x.clone().to(DEV)
-        call("rtdf_posconv_bf16", P(xo2), P(xb.to(DEV)), B, T, P(wb.to(DEV)), P(bias.to(DEV)), stream())
+        call("rtdf_posconv_bf16", P(xo2), P(dev(xb)), B, T, P(dev(wb)), P(dev(bias)), stream())
         d16 = float((xo2.cpu() - ref16).abs().max())
         out[f"B{B}_T{T}"] = (d32, d16)
         assert d32 <= 5e-5, out
@@ -209,7 +221,7 @@ def check_attention(impls=(0, 1)):
         qkv[:, : H * 64] *= 0.25
         ref32 = _attn_ref(qkv, B, T, H)
         o = torch.empty(B * T, H * 64, dtype=torch.float32, device=DEV)
-        call("rtdf_attention", P(qkv.to(DEV)), P(o), B, T, H, 0, 1, stream())
+        call("rtdf_attention", P(dev(qkv)), P(o), B, T, H, 0, 1, stream())
         d = float((o.cpu() - ref32).abs().max())
         out[f"B{B}_T{T}_H{H}_f32"] = d
         assert d <= 2e-5, out
@@ -217,7 +229,7 @@ def check_attention(impls=(0, 1)):
         ref16 = _attn_ref(qb, B, T, H)
         for impl in impls:
             o16 = torch.zeros(B * T, H * 64, dtype=torch.bfloat16, device=DEV)
-            call("rtdf_attention", P(qb.to(DEV)), P(o16), B, T, H, 1, impl, stream())
+            call("rtdf_attention", P(dev(qb)), P(o16), B, T, H, 1, impl, stream())
             d = float((o16.float().cpu() - ref16).abs().max())
             out[f"B{B}_T{T}_H{H}_bf16_impl{impl}"] = d
             assert d <= 0.03, out     # bf16 P and bf16 output rounding, |out| <~ 3
@@ -236,7 +248,7 @@ def check_graph_pool():
         k = ref.shape[1]
         o = torch.empty(B, k, D, dtype=torch.float32, device=DEV)
         io = torch.empty(B, k, dtype=torch.int32, device=DEV)
-        call("rtdf_graph_pool", P(h.to(DEV)), B, n, D, P(gp.proj.weight.detach().to(DEV)), P(gp.proj.bias.detach().to(DEV)),
+        call("rtdf_graph_pool", P(dev(h)), B, n, D, P(dev(gp.proj.weight.detach())), P(dev(gp.proj.bias.detach())),
              k, P(o), P(io), stream())
         same = bool((io.cpu().long() == idx).all())
         d = float((o.cpu() - ref).abs().max())
@@ -248,6 +260,6 @@ def check_graph_pool():
     o = torch.empty(1, 4, 32, device=DEV)
     io = torch.empty(1, 4, dtype=torch.int32, device=DEV)
     w = torch.ones(32)
-    call("rtdf_graph_pool", P(h.to(DEV)), 1, 8, 32, P(w.to(DEV)), P(torch.zeros(1).to(DEV)), 4, P(o), P(io), stream())
+    call("rtdf_graph_pool", P(dev(h)), 1, 8, 32, P(dev(w)), P(dev(torch.zeros(1))), 4, P(o), P(io), stream())
     assert io.cpu().tolist() == [[0, 1, 2, 3]], io
     return out

@@ -1,0 +1,64 @@
+"""GPU block / end-to-end parity against the CPU oracle and the committed golden vectors
+(produced by the reference's own model files; oracle/check_against_reference.py)."""
+import pytest
+
+from tests import e2e_checks as ec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_backend_block(precision):
+    ec.check_backend_block(precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frontend_block(precision):
+    ec.check_frontend_block(precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_e2e_xlsr_aasist_1s(precision):
+    ec.check_e2e(kind="XLSR_AASIST", precision=precision, B=2, N=16000)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_e2e_conformer_1s(precision):
+    ec.check_e2e(kind="ConformerModel", precision=precision, B=2, N=16000)
+
+
+def test_e2e_student_conformer_fixed_call():
+    ec.check_e2e(kind="MyModel", precision="bf16", B=2, N=16000, num_layers=2, fixed_call=True)
+
+
+@pytest.mark.parametrize("name,precision", [
+    ("xlsr_aasist_n64000_b2", "bf16"),
+    ("xlsr_aasist_n64600_b1", "bf16"),
+    ("xlsr_aasist_n16000_b2", "fp32"),
+    ("student6_aasist_n64000_b2", "bf16"),
+    ("student_mid4_aasist_n16000_b2", "fp32"),
+    ("conformer_n64600_b1", "bf16"),
+    ("conformer_n16000_b2", "fp32"),
+    ("student2_conformer_n16000_b2", "bf16"),
+])
+def test_golden_vectors_from_reference(name, precision):
+    ec.check_golden(name, precision=precision)
+
+
+def test_ragged_batches_preemphasis_determinism():
+    ec.check_ragged_and_quirks(precision="fp32")
+
+
+def test_errors_are_loud():
+    import torch
+    from tests.util import build_pair
+    _, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=1)
+    with pytest.raises(RuntimeError):
+        prod(torch.zeros(1, 16000))                       # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        prod.train()(torch.zeros(1, 16000, device="cuda"))  # training mode is not accelerated
+    prod.eval()
+    with pytest.raises((RuntimeError, ValueError)):
+        prod(torch.zeros(1, 100, device="cuda"))          # shorter than the conv receptive field
+    with pytest.raises(RuntimeError):
+        prod(torch.zeros(1, 16000 * 6, device="cuda"))    # T > 256 frames: outside the attention tile kernel

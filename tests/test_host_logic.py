@@ -1,0 +1,126 @@
+"""CPU: host-side mirror of the reference interface (state-dict contract, layer selection, error
+behaviour) and the sharding / gather logic (world_size 2 over gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests.util import pkg
+
+
+def test_state_dict_contract_matches_oracle_and_reference():
+    from oracle import models_ref as O
+    xa = pkg("models.xlsr_aasist")
+    cb = pkg("models.conformer_baseline")
+    ora = O.build("My_XLSR_AASIST", perturb=False, num_layers=2)
+    prod = xa.My_XLSR_AASIST("cpu", None, num_layers=2)
+    assert set(prod.state_dict()) == set(ora.state_dict())
+    for k, v in ora.state_dict().items():
+        assert prod.state_dict()[k].shape == v.shape, k
+    prod.load_state_dict(ora.state_dict(), strict=True)
+    orc = O.build("MyModel", perturb=False, num_layers=1)
+    prc = cb.MyModel("cpu", None, num_layers=1)
+    assert set(prc.state_dict()) == set(orc.state_dict())
+    # key spot checks from SURVEY.md App. A.5
+    keys = set(prod.state_dict())
+    for k in ("ssl_model.model.feature_extractor.conv_layers.0.0.weight",
+              "ssl_model.model.feature_extractor.conv_layers.6.2.1.bias",
+              "ssl_model.model.encoder.pos_conv.0.weight_g", "ssl_model.model.encoder.layers.1.self_attn.q_proj.weight",
+              "ssl_model.model.mask_emb", "encoder.1.0.bn1.weight", "encoder.2.0.conv_downsample.bias",
+              "HtrgGAT_layer_ST12.att_weightM", "pool_hT2.proj.weight", "pos_S", "master2", "out_layer.bias"):
+        assert k in keys, k
+    assert "conformer.encoder_blocks.0.attn.fn.rel_pos_emb.weight" in set(prc.state_dict())
+    assert prc.state_dict()["conformer.encoder_blocks.0.conv.net.4.conv.weight"].shape == (288, 1, 31)
+
+
+def test_layer_selection_and_errors():
+    fe = pkg("models.fe")
+    assert fe.middle_indices(24, 6) == list(range(9, 15))
+    m = fe.My_XLSR_FE("cpu", num_layers=3, order="last")
+    assert len(m.model.encoder.layers) == 3
+    full = fe.XLSR_FE("cpu")
+    assert len(full.model.encoder.layers) == 24 and full.out_dim == 1024
+    # the kept modules are the *same* objects in the requested order (fe.py:69-90)
+    c = fe.My_XLSR_FE("cpu", num_layers=2, order="custom", custom_order=[5, 1])
+    assert len(c.model.encoder.layers) == 2
+    with pytest.raises(ValueError):
+        fe.My_XLSR_FE("cpu", num_layers=0)
+    with pytest.raises(ValueError):
+        fe.My_XLSR_FE("cpu", num_layers=25)
+    with pytest.raises(ValueError):
+        fe.My_XLSR_FE("cpu", num_layers=2, order="custom")
+    with pytest.raises(ValueError):
+        fe.My_XLSR_FE("cpu", num_layers=2, order="custom", custom_order=(1, 2))
+
+
+def test_no_cpu_fallback_and_reference_typeerror():
+    xa = pkg("models.xlsr_aasist")
+    cb = pkg("models.conformer_baseline")
+    m = xa.My_XLSR_AASIST("cpu", None, num_layers=1).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 16000))
+    with pytest.raises(RuntimeError, match="eval"):
+        m.train()(torch.zeros(1, 16000))
+    with pytest.raises(RuntimeError):
+        m.GAT_layer_S(torch.zeros(1, 4, 64))           # sub-blocks run only inside the fused path
+    s = cb.MyModel("cpu", None, num_layers=1).eval()
+    with pytest.raises(TypeError):                      # conformer_baseline.py:98 as shipped
+        s(torch.zeros(1, 16000))
+
+
+def test_pretraining_heads_in_checkpoints_are_tolerated():
+    w2v = pkg("models.wav2vec2_params")
+    m = w2v.Wav2Vec2Model(layers=1)
+    sd = dict(m.state_dict())
+    sd["quantizer.vars"] = torch.zeros(3)
+    sd["final_proj.weight"] = torch.zeros(2, 2)
+    m.load_state_dict(sd, strict=True)
+
+
+def test_shard_ranges_cover_everything_once():
+    sc = pkg("scoring")
+    for n, w in ((180000, 8), (10, 4), (7, 8), (0, 2), (64, 1), (65, 2)):
+        seen = []
+        per = None
+        for r in range(w):
+            lo, hi, per = sc.shard_range(n, r, w)
+            assert 0 <= lo <= hi <= n and hi - lo <= per
+            seen += list(range(lo, hi))
+        assert seen == list(range(n))
+    assert sc.batch_ranges(3, 10, 4) == [(3, 7), (7, 10)]
+    with pytest.raises(ValueError):
+        sc.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n_items, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = pkg("scoring")
+    lo, hi, per = sc.shard_range(n_items, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32) * 0.5      # "score" of utterance i is i/2
+    out = sc.gather_scores(local, n_items, per)
+    ret[rank] = out.tolist()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [11, 8])
+def test_two_rank_gloo_gather_restores_global_order(n_items):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(world, port, n_items, ret), nprocs=world, join=True)
+    expect = [i * 0.5 for i in range(n_items)]
+    assert ret[0] == expect and ret[1] == expect

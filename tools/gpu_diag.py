@@ -30,6 +30,10 @@ CHECKS = [
     ("backend_block_bf16", "tests.e2e_checks", "check_backend_block", {"precision": "bf16"}),
     ("frontend_block_fp32", "tests.e2e_checks", "check_frontend_block", {"precision": "fp32"}),
     ("frontend_block_bf16", "tests.e2e_checks", "check_frontend_block", {"precision": "bf16"}),
+    ("frontend_64000_fp32_L1", "tests.e2e_checks", "check_frontend_block", {"precision": "fp32", "N": 64000, "kind": "My_XLSR_AASIST", "num_layers": 1}),
+    ("frontend_64000_bf16_L1", "tests.e2e_checks", "check_frontend_block", {"precision": "bf16", "N": 64000, "kind": "My_XLSR_AASIST", "num_layers": 1}),
+    ("frontend_64000_bf16_L24", "tests.e2e_checks", "check_frontend_block", {"precision": "bf16", "N": 64000}),
+    ("backend_block_fp32_64000", "tests.e2e_checks", "check_backend_block", {"precision": "fp32", "N": 64000, "B": 2}),
     ("e2e_aasist_fp32", "tests.e2e_checks", "check_e2e", {"precision": "fp32"}),
     ("e2e_aasist_bf16", "tests.e2e_checks", "check_e2e", {"precision": "bf16"}),
     ("e2e_conformer_fp32", "tests.e2e_checks", "check_e2e", {"kind": "ConformerModel", "precision": "fp32"}),

@@ -2,8 +2,9 @@
 //   warp 0      : TMA producer  (A tile 128 x BK, W tile BN x BK per stage, 128B/64B swizzle)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulators live in TMEM,
 //                 double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2..   : epilogue -- tcgen05.ld the accumulator (one row per thread), fused bias /
-//                 activation / residual / LayerNorm, vectorised global stores.
+//   warps 2..9  : epilogue -- tcgen05.ld the accumulator (one row per thread), fused bias / activation /
+//                 scale / LayerNorm, results staged in 128B-swizzled smem and written with TMA stores
+//                 (fp32 residual updates use the TMA reduce-add, so the SM never reads the residual).
 // smem stages are recycled through full/empty mbarriers; MMA completion is signalled with
 // tcgen05.commit.  Replaces the cuBLAS/cuDNN calls behind fairseq's Linear / Conv1d layers
 // (reference models/fe.py:19).
@@ -11,11 +12,19 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace rtdf {
 
 using namespace ptx;
+
+enum EpiMode {
+  EPI_DIRECT = 0,       // per-thread global loads/stores (any combination of outputs / residual)
+  EPI_TMA_F32 = 1,      // out_f32 = v                (TMA store)
+  EPI_TMA_F32_ADD = 2,  // out_f32 += v               (TMA reduce-add; in-place residual)
+  EPI_TMA_BF16 = 3,     // out_bf16 = v               (TMA store)
+};
 
 struct TcKernelParams {
   int rows_per_batch;
@@ -23,6 +32,7 @@ struct TcKernelParams {
   int num_kb;
   int tiles_n, tiles_m, total_tiles;
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
+  int epi_mode;
   TcEpilogue epi;
 };
 
@@ -55,22 +65,26 @@ int tc_profile_end(int variant, double* ms_total, double* flops_total, int* laun
 }
 
 constexpr int BM = 128;
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
 template <int BN, int BK>
 struct TcCfg {
   static constexpr bool kLN = (BN == 512);
   static constexpr int kAcc = kLN ? 1 : 2;             // TMEM accumulator stages
-  static constexpr int kEpiWarps = kLN ? 4 : 8;        // epilogue warps (2 per TMEM lane quarter when 8)
+  static constexpr int kEpiWarps = 8;                  // 2 warps per TMEM lane quarter (column halves)
   static constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0: TMA, warp 1: MMA, rest: epilogue
   static constexpr int kTmemCols = kLN ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kParamBytes = kLN ? 3 * 512 * 4 : 2 * BN * 4;  // LN: bias|gamma|beta ; plain: bias[2][BN]
-  static constexpr int kBudget = 224 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kParamBytes;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;                 // one 32-row x 128-byte box per warp
+  // LN: bias|gamma|beta [512] + partial stats [2 bufs][2 halves][128 rows] float2 ; plain: bias[2][BN]
+  static constexpr int kParamBytes = kLN ? (3 * 512 * 4 + 2 * 2 * 128 * 8) : 2 * BN * 4;
+  static constexpr int kFixed = kStagingBytes + 256 /*barriers*/ + kParamBytes;
+  static constexpr int kStagesRaw = (kMaxSmem - kFixed) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kParamBytes;
+  static constexpr int kNeeded = kStages * kStageBytes + kFixed;         // measured from a 1024-aligned base
+  static constexpr int kSmemBytes = kNeeded + 1024 > kMaxSmem ? kMaxSmem : kNeeded + 1024;
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, int bk) {
@@ -85,10 +99,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, int bk) {
   return d;
 }
 
-// ---- plain epilogue: one accumulator row per thread, 32 columns per step; bias comes from smem ----
-__device__ __forceinline__ void epilogue_store32(const TcEpilogue& e, const uint32_t* acc, const float* s_bias,
-                                                 long long row, int col, int N, bool row_ok) {
-  float o[32];
+// v = act(acc + bias) * scale for 32 consecutive columns of this thread's row
+__device__ __forceinline__ void epilogue_math32(const TcEpilogue& e, const uint32_t* acc, const float* s_bias, float* o) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(acc[i]) + s_bias[i];
   if (e.act == ACT_GELU) {
@@ -105,26 +117,20 @@ __device__ __forceinline__ void epilogue_store32(const TcEpilogue& e, const uint
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] *= e.scale;
   }
+}
+
+// direct (non-TMA) output path: per-thread row-strided global accesses
+__device__ __forceinline__ void epilogue_direct32(const TcEpilogue& e, float* o, long long row, int col, int N, bool row_ok) {
   if (!row_ok) return;
   const bool full = col + 32 <= N;
   if (e.resid) {
     const float* r = e.resid + row * e.ldr + col;
-    if (full) {
-      float4 t[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(r + 4 * i);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[4 * i] += t[i].x; o[4 * i + 1] += t[i].y; o[4 * i + 2] += t[i].z; o[4 * i + 3] += t[i].w;
+    for (int i = 0; i < 32; i += 4)
+      if (full || col + i + 4 <= N) {
+        const float4 t = *reinterpret_cast<const float4*>(r + i);
+        o[i] += t.x; o[i + 1] += t.y; o[i + 2] += t.z; o[i + 3] += t.w;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        if (col + i + 4 <= N) {
-          const float4 t = *reinterpret_cast<const float4*>(r + i);
-          o[i] += t.x; o[i + 1] += t.y; o[i + 2] += t.z; o[i + 3] += t.w;
-        }
-    }
   }
   if (e.out_f32) {
     float* p = e.out_f32 + row * e.ld_f32 + col;
@@ -142,13 +148,29 @@ __device__ __forceinline__ void epilogue_store32(const TcEpilogue& e, const uint
   }
 }
 
+// Stage one 128-byte row per lane into this warp's 32 x 128 B box (SWIZZLE_128B pattern expected by the
+// TMA store: 16-byte chunk j of row r lives at chunk j ^ (r & 7)).
+__device__ __forceinline__ void stage_row_f32(uint8_t* box, int lane, const float* o) {
+  uint8_t* rowp = box + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_row_bf16(uint8_t* box, int lane, const float* o /*64 values*/) {
+  uint8_t* rowp = box + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+        make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                   pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+}
+
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (n-tile fastest so that concurrently
-// running CTAs share A rows in L2).  The smem ring runs across tile boundaries; the accumulator is
-// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// running CTAs share A rows in L2).  The smem ring runs across tile boundaries.
 template <int BN, int BK>
 __global__ void __launch_bounds__(TcCfg<BN, BK>::kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const TcKernelParams p) {
+               const __grid_constant__ CUtensorMap mapC, const TcKernelParams p) {
   using Cfg = TcCfg<BN, BK>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kLN = Cfg::kLN;
@@ -157,16 +179,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
-  // barrier layout: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  if (threadIdx.x == 0 && (smem_base - smem_u32(smem_raw)) + Cfg::kNeeded > Cfg::kSmemBytes) {
+    printf("rtdf: tc_gemm smem layout does not fit (base misaligned by %u)\n", smem_base - smem_u32(smem_raw));
+    __trap();
+  }
+  // layout: stages | epilogue staging boxes (1024-aligned) | barriers (256 B) | params
+  constexpr int kOffStaging = kStages * Cfg::kStageBytes;
+  constexpr int kOffBars = kOffStaging + Cfg::kStagingBytes;
+  constexpr int kOffParams = kOffBars + 256;
+  const uint32_t bar_base = smem_base + kOffBars;
+  // barriers: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 4));
-  float* s_params = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + 256);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBars + 8 * (2 * kStages + 4));
+  float* s_params = reinterpret_cast<float*>(smem_gen + kOffParams);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,6 +203,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
+    if (p.epi_mode != EPI_DIRECT) prefetch_tmap(&mapC);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -258,17 +288,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4; with 8 warps the column range is split in two =====
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0 .. kEpiThreads-1
+    uint8_t* box_gen = smem_gen + kOffStaging + (warp - 2) * 4096;
+    const uint32_t box = smem_base + kOffStaging + (warp - 2) * 4096;
+    const int mode = p.epi_mode;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
       const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
       const int m0 = m_tile * BM, n0 = n_tile * BN;
       const int a = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
-      const int row_local = m0 + q * 32 + lane;
+      const int row0 = m0 + q * 32;                 // first row of this warp inside the batch
+      const int row_local = row0 + lane;
       const bool row_ok = row_local < p.rows_per_batch;
       const long long row = static_cast<long long>(batch) * p.rows_per_batch + row_local;
       if (!kLN) {
@@ -282,69 +316,106 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (kLN ? 0 : a * BN);
       if (!kLN) {
-        constexpr int kColsPerWarp = BN / (Cfg::kEpiWarps / 4);
+        constexpr int kColsPerWarp = BN / 2;
         const float* sb = s_params + a * BN;
+        const int c_begin = half * kColsPerWarp, c_end = c_begin + kColsPerWarp;
+        if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
 #pragma unroll 1
-        for (int c = half * kColsPerWarp; c < (half + 1) * kColsPerWarp; c += 32) {
-          if (n0 + c >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld32(t_row + c, r);
-          tmem_ld_wait();
-          epilogue_store32(p.epi, r, sb + c, row, n0 + c, p.N, row_ok);
+          for (int c = c_begin; c < c_end; c += 64) {
+            if (n0 + c >= p.N) break;  // warp-uniform
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + c, r0);
+            tmem_ld32(t_row + c + 32, r1);
+            tmem_ld_wait();
+            float o[64];
+            epilogue_math32(p.epi, r0, sb + c, o);
+            epilogue_math32(p.epi, r1, sb + c + 32, o + 32);
+            if (lane == 0) tma_store_wait_read<0>();   // previous store out of this box has drained
+            __syncwarp();
+            stage_row_bf16(box_gen, lane, o);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.rows_per_batch) {
+              tma_store_3d(&mapC, box, n0 + c, row0, batch);
+              tma_store_commit();
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = c_begin; c < c_end; c += 32) {
+            if (n0 + c >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(t_row + c, r);
+            tmem_ld_wait();
+            float o[32];
+            epilogue_math32(p.epi, r, sb + c, o);
+            if (mode == EPI_TMA_F32 || mode == EPI_TMA_F32_ADD) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+              stage_row_f32(box_gen, lane, o);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && row0 < p.rows_per_batch) {
+                if (mode == EPI_TMA_F32_ADD) tma_reduce_add_3d(&mapC, box, n0 + c, row0, batch);
+                else tma_store_3d(&mapC, box, n0 + c, row0, batch);
+                tma_store_commit();
+              }
+            } else {
+              epilogue_direct32(p.epi, o, row, n0 + c, p.N, row_ok);
+            }
+          }
         }
       } else {
-        // y = act(LayerNorm_512(acc + bias)); two-pass statistics straight out of TMEM
+        // y = act(LayerNorm_512(acc + bias)).  Two warps share a row (256 columns each): one TMEM pass for
+        // (sum, sum of squares), partials exchanged through smem, one pass to normalise / activate / store.
         const float* s_bias = s_params;
         const float* s_gamma = s_params + 512;
         const float* s_beta = s_params + 1024;
-        float sum = 0.f;
-        for (int c = 0; c < 512; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + s_bias[c + i];
-        }
-        const float mean = sum * (1.0f / 512.0f);
-        float ssq = 0.f;
-        for (int c = 0; c < 512; c += 32) {
+        float2* s_stat = reinterpret_cast<float2*>(s_params + 1536) + (lt & 1) * 256;   // [half][128 rows]
+        const int c_begin = half * 256;
+        float sum = 0.f, ssq = 0.f;
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + 256; c += 32) {
           uint32_t r[32];
           tmem_ld32(t_row + c, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float d = __uint_as_float(r[i]) + s_bias[c + i] - mean;
-            ssq += d * d;
+            const float v = __uint_as_float(r[i]) + s_bias[c + i];
+            sum += v;
+            ssq = fmaf(v, v, ssq);
           }
         }
-        const float rstd = rsqrtf(ssq * (1.0f / 512.0f) + p.epi.ln_eps);
-        for (int c = 0; c < 512; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c, r);
+        s_stat[half * 128 + q * 32 + lane] = make_float2(sum, ssq);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        const float2 other = s_stat[(half ^ 1) * 128 + q * 32 + lane];
+        const float mean = (sum + other.x) * (1.0f / 512.0f);
+        const float var = fmaxf((ssq + other.y) * (1.0f / 512.0f) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.epi.ln_eps);
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + 256; c += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + c, r0);
+          tmem_ld32(t_row + c + 32, r1);
           tmem_ld_wait();
-          float o[32];
+          float o[64];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            o[i] = (__uint_as_float(r[i]) + s_bias[c + i] - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
+          for (int i = 0; i < 32; ++i) {
+            o[i] = (__uint_as_float(r0[i]) + s_bias[c + i] - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
+            o[32 + i] = (__uint_as_float(r1[i]) + s_bias[c + 32 + i] - mean) * rstd * s_gamma[c + 32 + i] + s_beta[c + 32 + i];
+          }
           if (p.epi.act == ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = gelu_fast(o[i]);
+            for (int i = 0; i < 64; ++i) o[i] = gelu_fast(o[i]);
           }
-          if (row_ok) {
-            if (p.epi.out_bf16) {
-              bf16* dst = p.epi.out_bf16 + row * p.epi.ld_bf16 + c;
-#pragma unroll
-              for (int i = 0; i < 32; i += 8)
-                *reinterpret_cast<uint4*>(dst + i) =
-                    make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
-                               pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
-            }
-            if (p.epi.out_f32) {
-              float* dst = p.epi.out_f32 + row * p.epi.ld_f32 + c;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-            }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          stage_row_bf16(box_gen, lane, o);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.rows_per_batch) {
+            tma_store_3d(&mapC, box, c, row0, batch);
+            tma_store_commit();
           }
         }
       }
@@ -352,6 +423,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
     }
+    if (lane == 0) tma_store_wait_all<0>();   // outstanding TMA stores complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -361,12 +433,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+static bool force_direct_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_TC_EPILOGUE");
+    v = (e && e[0] == 'd') ? 1 : 0;   // RTDF_TC_EPILOGUE=direct disables the TMA-store epilogue (debug / A-B runs)
+  }
+  return v == 1;
+}
+
 template <int BN, int BK>
 static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, int mode,
                           const TcEpilogue& epi) {
   using Cfg = TcCfg<BN, BK>;
   static_assert(Cfg::kStages >= 2, "need at least two stages");
-  CUtensorMap mapA, mapB;
+  static_assert(8 * (2 * Cfg::kStages + 5) <= 256, "barrier block too small");
+  CUtensorMap mapA, mapB, mapC;
   {
     uint64_t dims[3] = {(uint64_t)A.k_extent, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
     uint64_t strides[2] = {(uint64_t)A.row_stride * 2, (uint64_t)(A.batches > 1 ? A.batch_stride : A.row_stride * A.rows_per_batch) * 2};
@@ -394,6 +476,33 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   }
   p.epi = epi;
+  // ---- choose the output path: a single output tensor goes through TMA stores ----
+  p.epi_mode = EPI_DIRECT;
+  const bool one_f32 = epi.out_f32 && !epi.out_bf16 && (epi.ld_f32 % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(epi.out_f32) % 16 == 0);
+  const bool one_bf16 = epi.out_bf16 && !epi.out_f32 && !epi.resid && (epi.ld_bf16 % 8 == 0) &&
+                        (reinterpret_cast<uintptr_t>(epi.out_bf16) % 16 == 0);
+  if (Cfg::kLN) {
+    RTDF_REQUIRE(one_bf16, "tc_gemm: the LayerNorm variant writes exactly one bf16 output (16-byte aligned rows)");
+    p.epi_mode = EPI_TMA_BF16;
+  } else if (!force_direct_epilogue()) {
+    if (one_f32 && !epi.resid) p.epi_mode = EPI_TMA_F32;
+    else if (one_f32 && epi.resid == epi.out_f32 && epi.ldr == epi.ld_f32) p.epi_mode = EPI_TMA_F32_ADD;
+    else if (one_bf16 && BN >= 128) p.epi_mode = EPI_TMA_BF16;
+  }
+  if (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)epi.ld_f32 * 4, (uint64_t)epi.ld_f32 * 4 * (uint64_t)A.rows_per_batch};
+    uint32_t box[3] = {32, 32, 1};
+    RTDF_TRY(make_tmap_f32(&mapC, epi.out_f32, 3, dims, strides, box, TMAP_SW128));
+  } else if (p.epi_mode == EPI_TMA_BF16) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)epi.ld_bf16 * 2, (uint64_t)epi.ld_bf16 * 2 * (uint64_t)A.rows_per_batch};
+    uint32_t box[3] = {64, 32, 1};
+    RTDF_TRY(make_tmap_bf16(&mapC, epi.out_bf16, 3, dims, strides, box, TMAP_SW128));
+  } else {
+    mapC = mapA;  // unused
+  }
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
@@ -405,7 +514,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     rec.variant = BN + (BK == 32 ? 1 : 0);
     RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
-  tc_gemm_kernel<BN, BK><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mapA, mapB, p);
+  tc_gemm_kernel<BN, BK><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mapA, mapB, mapC, p);
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));

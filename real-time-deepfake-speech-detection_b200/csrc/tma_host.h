@@ -13,5 +13,8 @@ enum TmapSwizzle { TMAP_SW128 = 0, TMAP_SW64 = 1 };
 // negative).  Rows of a box are box[0] elements = 128 B (SW128) or 64 B (SW64).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw);
+// same for fp32 tensors (TMA store / reduce-add targets)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, TmapSwizzle sw);
 
 }  // namespace rtdf

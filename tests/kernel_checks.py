@@ -143,10 +143,16 @@ def check_gemm_bf16(variants=(64, 128, 256)):
             ref = F.gelu(base + b) * 0.5 + R
             d1 = float((o32.cpu() - ref).abs().max())
             d2 = float((o16.float().cpu() - ref).abs().max())
-            out[f"{M}x{N}x{K}_v{v}"] = (d0, d1, d2)
+            o_in = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=0.5, resid=R.to(DEV), variant=v, inplace=True)
+            d3 = float((o_in.cpu() - ref).abs().max())
+            o_b = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=0.5, out="bf16", variant=v)
+            d4 = float((o_b.float().cpu() - F.gelu(base + b) * 0.5).abs().max())
+            out[f"{M}x{N}x{K}_v{v}"] = (d0, d1, d2, d3, d4)
             assert d0 <= 2e-3, out     # fp32 accumulation of exact bf16 products, different summation order
             assert d1 <= 2e-3, out
             assert d2 <= 0.05, out     # bf16 output rounding
+            assert d3 <= 2e-3, out     # in-place residual update (TMA reduce-add)
+            assert d4 <= 0.05, out     # bf16-only output (TMA store)
     return out
 
 

@@ -35,9 +35,13 @@ def call(name, *args):
     nat.check(getattr(lib, name)(*args), name)
 
 
-def gemm_bf16(A, W, bias=None, act=0, scale=1.0, resid=None, out="f32", variant=256):
+def gemm_bf16(A, W, bias=None, act=0, scale=1.0, resid=None, out="f32", variant=256, inplace=False):
     M, K = A.shape
     N = W.shape[0]
+    if inplace:   # x += act(A W^T + b) * scale, updated in place (TMA reduce-add path)
+        x = resid.clone()
+        call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, scale, P(x), P(x), None, variant, stream())
+        return x
     o32 = torch.empty(M, N, dtype=torch.float32, device=A.device) if out in ("f32", "both") else None
     o16 = torch.empty(M, N, dtype=torch.bfloat16, device=A.device) if out in ("bf16", "both") else None
     call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, scale, P(resid), P(o32), P(o16), variant, stream())

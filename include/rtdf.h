@@ -123,6 +123,9 @@ int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, con
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Total number of kernels this library has launched in the calling process. */
 long long rtdf_launch_count(void);
+/* Timing A/B switch: evaluate the GELU of the tensor-core epilogues with 4 = hardware-tanh form, 5 = A&S 7.1.26
+ * erf; 0 restores the default (sigmoid-of-quintic fit of the erf GELU, |err| <= 2.6e-5). */
+int rtdf_debug_gelu_variant(int act);
 /* Bracket a region: every tcgen05 GEMM launch in it is timed with CUDA events on its own stream.
  * rtdf_profile_end sums duration (ms) and algorithmic FLOPs (2*M*N*K) of the launches of one tile
  * variant (64|128|256|512|513, or -1 for all). */

@@ -136,6 +136,10 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
 }
 
 long long rtdf_launch_count(void) { return launch_count(); }
+int rtdf_debug_gelu_variant(int act) {
+  tc_set_gelu_variant(act);
+  return RTDF_OK;
+}
 int rtdf_profile_begin(void) {
   tc_profile_begin();
   return RTDF_OK;

@@ -73,6 +73,72 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erf_x = copysignf(1.0f - erfc_z, x);
   return 0.5f * x * (1.0f + erf_x);
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two lanes per issue slot) -----------
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// GELU(x) = x * Phi(x) with Phi(x) ~= sigmoid(2 x (c1 + c3 x^2 + c5 x^4)); the odd polynomial is a minimax
+// fit of the erf form (max |error| of the whole GELU 2.6e-5 over R, tools/fit_gelu.py), evaluated on two
+// values per FFMA2 issue slot plus EX2 + RCP on the MUFU pipe.  -2*log2(e) is folded into the coefficients;
+// x^2 is clamped to 64 (Phi(8) == 1 in fp32) so the quintic never turns over.
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float k = -2.8853900817779268f;   // -2 / ln 2
+  float2 s = mul2(x, x);
+  s.x = fminf(s.x, 64.0f);
+  s.y = fminf(s.y, 64.0f);
+  float2 p = fma2(make_float2(k * -0.0003515189394188129f, k * -0.0003515189394188129f), s,
+                  make_float2(k * 0.03700565997219061f, k * 0.03700565997219061f));
+  p = fma2(p, s, make_float2(k * 0.7975078680535282f, k * 0.7975078680535282f));
+  const float2 u = mul2(x, p);
+  const float2 d = add2(make_float2(ex2_approx(u.x), ex2_approx(u.y)), make_float2(1.0f, 1.0f));
+  return mul2(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+}
+// tanh form on the hardware tanh (1 MUFU per value, |error| <= ~5e-4: only for A/B timing runs)
+__device__ __forceinline__ float2 gelu2_tanh(float2 x) {
+  const float2 s = mul2(x, x);
+  const float2 p = fma2(make_float2(0.034701004943096476f, 0.034701004943096476f), s,
+                        make_float2(0.8001568294135658f, 0.8001568294135658f));
+  const float2 y = mul2(x, p);
+  const float2 h = mul2(x, make_float2(0.5f, 0.5f));
+  return fma2(h, make_float2(tanh_approx(y.x), tanh_approx(y.y)), h);
+}
+__device__ __forceinline__ float gelu_sig(float x) { return gelu2(make_float2(x, x)).x; }
+
 __device__ __forceinline__ float selu_f(float x) {
   const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
   return x > 0.f ? scale * x : scale * alpha * expm1f(x);
@@ -80,10 +146,14 @@ __device__ __forceinline__ float selu_f(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
 
-enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SWISH = 2, ACT_SELU = 3 };
+// ACT_GELU_TANH / ACT_GELU_AS select alternative GELU evaluations in the tensor-core epilogues (A/B timing);
+// everywhere else they mean the exact erf GELU.
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SWISH = 2, ACT_SELU = 3, ACT_GELU_TANH = 4, ACT_GELU_AS = 5 };
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case ACT_GELU: return gelu_erf(x);
+    case ACT_GELU:
+    case ACT_GELU_TANH:
+    case ACT_GELU_AS: return gelu_erf(x);
     case ACT_SWISH: return swish_f(x);
     case ACT_SELU: return selu_f(x);
     default: return x;

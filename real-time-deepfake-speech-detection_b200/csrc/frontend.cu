@@ -99,8 +99,10 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c,
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
 }
 
+constexpr int kConv0FramesPerCta = 256;   // 8 warps x 8 groups of 4 frames: the 26 KB parameter block is loaded once
+
 template <typename TOut>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              float eps, TOut* __restrict__ out) {
@@ -114,68 +116,76 @@ conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restri
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int t0 = (blockIdx.x * 8 + warp) * 4;
-  if (t0 >= L1) return;
   const float* xb = wav + (long long)b * N;
-  // 4 frames need samples [5*t0, 5*t0 + 25)
-  float xv = 0.f;
-  {
-    const int i = 5 * t0 + lane;
-    if (lane < 25 && i < N) xv = xb[i];
-  }
-  float acc[4][16];
+  // lane owns channels {j*128 + lane*4 + e}: 16 channels as 8 packed pairs
+  for (int g = warp; g < kConv0FramesPerCta / 4; g += 8) {
+    const int t0 = blockIdx.x * kConv0FramesPerCta + g * 4;
+    if (t0 >= L1) break;
+    // 4 frames need samples [5*t0, 5*t0 + 25)
+    float xv = 0.f;
+    {
+      const int i = 5 * t0 + lane;
+      if (lane < 25 && i < N) xv = xb[i];
+    }
+    float2 acc[4][8];
 #pragma unroll
-  for (int f = 0; f < 4; ++f)
+    for (int j = 0; j < 4; ++j) {
+      const float4 bv = *reinterpret_cast<const float4*>(&sw[10][j * 128 + lane * 4]);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[f][c] = 0.f;
+      for (int f = 0; f < 4; ++f) {
+        acc[f][2 * j] = make_float2(bv.x, bv.y);
+        acc[f][2 * j + 1] = make_float2(bv.z, bv.w);
+      }
+    }
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    float4 w[4];
+    for (int k = 0; k < 10; ++k) {
+      float4 w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&sw[k][j * 128 + lane * 4]);
+      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&sw[k][j * 128 + lane * 4]);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        const float x = __shfl_sync(0xffffffffu, xv, 5 * f + k);
+        const float2 x2 = make_float2(x, x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[f][2 * j] = fma2(x2, make_float2(w[j].x, w[j].y), acc[f][2 * j]);
+          acc[f][2 * j + 1] = fma2(x2, make_float2(w[j].z, w[j].w), acc[f][2 * j + 1]);
+        }
+      }
+    }
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      const float x = __shfl_sync(0xffffffffu, xv, 5 * f + k);
+      float2 s2 = acc[f][0];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[f][j * 4 + 0] = fmaf(x, w[j].x, acc[f][j * 4 + 0]);
-        acc[f][j * 4 + 1] = fmaf(x, w[j].y, acc[f][j * 4 + 1]);
-        acc[f][j * 4 + 2] = fmaf(x, w[j].z, acc[f][j * 4 + 2]);
-        acc[f][j * 4 + 3] = fmaf(x, w[j].w, acc[f][j * 4 + 3]);
+      for (int c = 1; c < 8; ++c) s2 = add2(s2, acc[f][c]);
+      const float mean = warp_sum(s2.x + s2.y) * (1.0f / 512.0f);
+      const float2 nm2 = make_float2(-mean, -mean);
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        acc[f][c] = add2(acc[f][c], nm2);
+        q2 = fma2(acc[f][c], acc[f][c], q2);
       }
-    }
-  }
+      const float rstd = rsqrtf(warp_sum(q2.x + q2.y) * (1.0f / 512.0f) + eps);
+      const float2 rstd2 = make_float2(rstd, rstd);
+      const int t = t0 + f;
+      if (t < L1) {
+        TOut* o = out + ((long long)b * L1 + t) * 512;
 #pragma unroll
-  for (int f = 0; f < 4; ++f) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        acc[f][j * 4 + e] += sw[10][j * 128 + lane * 4 + e];
-        s += acc[f][j * 4 + e];
-      }
-    const float mean = warp_sum(s) * (1.0f / 512.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float d = acc[f][c] - mean;
-      q += d * d;
-    }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 512.0f) + eps);
-    const int t = t0 + f;
-    if (t < L1) {
-      TOut* o = out + ((long long)b * L1 + t) * 512;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = j * 128 + lane * 4 + e;
-          const float y = (acc[f][j * 4 + e] - mean) * rstd * sw[11][c] + sw[12][c];
-          r[e] = sizeof(TOut) == 2 ? gelu_fast(y) : gelu_erf(y);   // bf16 output: A&S erf (1.5e-7) suffices
+        for (int j = 0; j < 4; ++j) {
+          const float4 gv = *reinterpret_cast<const float4*>(&sw[11][j * 128 + lane * 4]);
+          const float4 bv = *reinterpret_cast<const float4*>(&sw[12][j * 128 + lane * 4]);
+          float2 y0 = fma2(acc[f][2 * j], mul2(make_float2(gv.x, gv.y), rstd2), make_float2(bv.x, bv.y));
+          float2 y1 = fma2(acc[f][2 * j + 1], mul2(make_float2(gv.z, gv.w), rstd2), make_float2(bv.z, bv.w));
+          if (sizeof(TOut) == 2) {   // bf16 output: the fitted GELU (|err| <= 2.6e-5) is far below the rounding step
+            y0 = gelu2(y0);
+            y1 = gelu2(y1);
+          } else {
+            y0 = make_float2(gelu_erf(y0.x), gelu_erf(y0.y));
+            y1 = make_float2(gelu_erf(y1.x), gelu_erf(y1.y));
+          }
+          store4<TOut>(o + j * 128 + lane * 4, y0.x, y0.y, y1.x, y1.y);
         }
-        store4<TOut>(o + j * 128 + lane * 4, r[0], r[1], r[2], r[3]);
       }
     }
   }
@@ -186,7 +196,7 @@ int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
   RTDF_REQUIRE(wav && w_t && gamma && beta && N >= 10 && B > 0 && B <= 65535, "conv0: bad arguments");
   RTDF_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "conv0: exactly one output must be given");
   const int L1 = (N - 10) / 5 + 1;
-  dim3 grid(ceil_div(L1, 32), B);
+  dim3 grid(ceil_div(L1, kConv0FramesPerCta), B);
   if (out_f32)
     conv0_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_f32);
   else

@@ -101,9 +101,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, int bk) {
 
 // v = act(acc + bias) * scale for 32 consecutive columns of this thread's row
 __device__ __forceinline__ void epilogue_math32(const TcEpilogue& e, const uint32_t* acc, const float* s_bias, float* o) {
+  float2* o2 = reinterpret_cast<float2*>(o);
+  const float2* b2 = reinterpret_cast<const float2*>(s_bias);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(acc[i]) + s_bias[i];
+  for (int i = 0; i < 16; ++i)
+    o2[i] = add2(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])), b2[i]);
   if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o2[i] = gelu2(o2[i]);
+  } else if (e.act == ACT_GELU_TANH) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o2[i] = gelu2_tanh(o2[i]);
+  } else if (e.act == ACT_GELU_AS) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = gelu_fast(o[i]);
   } else if (e.act == ACT_SWISH) {
@@ -327,7 +336,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tmem_ld32(t_row + c, r0);
             tmem_ld32(t_row + c + 32, r1);
             tmem_ld_wait();
-            float o[64];
+            __align__(8) float o[64];
             epilogue_math32(p.epi, r0, sb + c, o);
             epilogue_math32(p.epi, r1, sb + c + 32, o + 32);
             if (lane == 0) tma_store_wait_read<0>();   // previous store out of this box has drained
@@ -347,7 +356,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             uint32_t r[32];
             tmem_ld32(t_row + c, r);
             tmem_ld_wait();
-            float o[32];
+            __align__(8) float o[32];
             epilogue_math32(p.epi, r, sb + c, o);
             if (mode == EPI_TMA_F32 || mode == EPI_TMA_F32_ADD) {
               if (lane == 0) tma_store_wait_read<0>();
@@ -373,38 +382,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float* s_beta = s_params + 1024;
         float2* s_stat = reinterpret_cast<float2*>(s_params + 1536) + (lt & 1) * 256;   // [half][128 rows]
         const int c_begin = half * 256;
-        float sum = 0.f, ssq = 0.f;
+        float2 sum2 = make_float2(0.f, 0.f), ssq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + 256; c += 32) {
           uint32_t r[32];
           tmem_ld32(t_row + c, r);
           tmem_ld_wait();
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]) + s_bias[c + i];
-            sum += v;
-            ssq = fmaf(v, v, ssq);
+          for (int i = 0; i < 16; ++i) {
+            const float2 v = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]);
+            sum2 = add2(sum2, v);
+            ssq2 = fma2(v, v, ssq2);
           }
         }
+        const float sum = sum2.x + sum2.y, ssq = ssq2.x + ssq2.y;
         s_stat[half * 128 + q * 32 + lane] = make_float2(sum, ssq);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         const float2 other = s_stat[(half ^ 1) * 128 + q * 32 + lane];
         const float mean = (sum + other.x) * (1.0f / 512.0f);
         const float var = fmaxf((ssq + other.y) * (1.0f / 512.0f) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.epi.ln_eps);
+        const float2 rstd2 = make_float2(rstd, rstd), nmean2 = make_float2(-mean, -mean);
 #pragma unroll 1
         for (int c = c_begin; c < c_begin + 256; c += 64) {
           uint32_t r0[32], r1[32];
           tmem_ld32(t_row + c, r0);
           tmem_ld32(t_row + c + 32, r1);
           tmem_ld_wait();
-          float o[64];
+          __align__(8) float o[64];
+          float2* o2 = reinterpret_cast<float2*>(o);
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c);
+          const float2* g2 = reinterpret_cast<const float2*>(s_gamma + c);
+          const float2* be2 = reinterpret_cast<const float2*>(s_beta + c);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            o[i] = (__uint_as_float(r0[i]) + s_bias[c + i] - mean) * rstd * s_gamma[c + i] + s_beta[c + i];
-            o[32 + i] = (__uint_as_float(r1[i]) + s_bias[c + 32 + i] - mean) * rstd * s_gamma[c + 32 + i] + s_beta[c + 32 + i];
+            const uint32_t* r = i < 16 ? r0 : r1;
+            const int j = i & 15;
+            const float2 v = add2(add2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), b2[i]), nmean2);
+            o2[i] = fma2(v, mul2(g2[i], rstd2), be2[i]);
           }
           if (p.epi.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o2[i] = gelu2(o2[i]);
+          } else if (p.epi.act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o2[i] = gelu2_tanh(o2[i]);
+          } else if (p.epi.act == ACT_GELU_AS) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) o[i] = gelu_fast(o[i]);
           }
@@ -432,6 +456,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
+
+static int g_gelu_override = 0;
+void tc_set_gelu_variant(int act) { g_gelu_override = (act == ACT_GELU_TANH || act == ACT_GELU_AS) ? act : 0; }
 
 static bool force_direct_epilogue() {
   static int v = -1;
@@ -476,6 +503,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   }
   p.epi = epi;
+  if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   // ---- choose the output path: a single output tensor goes through TMA stores ----
   p.epi_mode = EPI_DIRECT;
   const bool one_f32 = epi.out_f32 && !epi.out_bf16 && (epi.ld_f32 % 4 == 0) &&

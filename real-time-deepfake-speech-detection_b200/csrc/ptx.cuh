@@ -172,6 +172,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// SWIZZLE_64B canonical K-major layout (8-row x 64-byte atoms, atoms 512 B apart): K extent = 32 bf16.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;            // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulate.
 // a_mn / b_mn: 0 = K-major operand, 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {

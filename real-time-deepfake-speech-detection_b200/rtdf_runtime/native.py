@@ -50,6 +50,7 @@ SIGNATURES = {
     "rtdf_posconv_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rtdf_launch_count": (c_longlong, []),
+    "rtdf_debug_gelu_variant": (c_int, [c_int]),
     "rtdf_profile_begin": (c_int, []),
     "rtdf_profile_end": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "rtdf_graph_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -156,6 +156,22 @@ def check_gemm_bf16(variants=(64, 128, 256)):
     return out
 
 
+def check_gelu_epilogue():
+    """The tensor-core epilogue GELUs against the exact erf GELU on a dense grid (identity GEMM, fp32 output).
+    act 1 = sigmoid-of-quintic fit (product default), 4 = hardware-tanh form, 5 = A&S 7.1.26 erf."""
+    M, K = 2048, 64
+    xs = torch.linspace(-12.0, 12.0, M * K).to(torch.bfloat16).reshape(M, K)     # bf16-exact inputs
+    eye = torch.eye(K).to(torch.bfloat16)
+    ref = F.gelu(xs.double()).float()
+    out = {}
+    for act, tol in ((1, 4e-5), (4, 1.5e-3), (5, 2e-6)):
+        o = gemm_bf16(xs.to(DEV), eye.to(DEV), act=act, variant=64)
+        d = float((o.cpu() - ref).abs().max())
+        out[f"act{act}"] = d
+        assert d <= tol, out
+    return out
+
+
 def _conv_ref(x, w, b, gamma, beta, stride):
     y = F.conv1d(x.transpose(1, 2), w, b, stride=stride)             # (B,512,L)
     return F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))

@@ -37,6 +37,10 @@ def test_gemm_bf16_tcgen05(variant):
     kc.check_gemm_bf16(variants=(variant,))
 
 
+def test_gelu_epilogue_accuracy():
+    kc.check_gelu_epilogue()
+
+
 @pytest.mark.parametrize("variant", [512, 513])
 def test_conv1d_implicit_gemm_ln_gelu(variant):
     kc.check_conv1d_tc(variants=(variant,))

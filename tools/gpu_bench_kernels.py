@@ -49,6 +49,10 @@ def main():
         for v in (256, 128):
             ms = timeit(lambda: call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, 1.0, None, None, P(out), v, stream()))
             print(f"gemm {name:9s} N={N:4d} K={K:4d} variant {v}: {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s")
+        if act == 1:
+            for gv, gname in ((4, "hw-tanh"), (5, "A&S erf")):
+                ms = timeit(lambda: call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), gv, 1.0, None, None, P(out), 256, stream()))
+                print(f"gemm {name:9s} N={N:4d} K={K:4d} variant 256 gelu={gname}: {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s")
         ref = timeit(lambda: torch.nn.functional.linear(A, W))
         print(f"     torch/cuBLAS same shape (no epilogue):      {ref:7.3f} ms  {2.0 * M * N * K / ref / 1e9:8.1f} TFLOP/s")
     # conv feature encoder layers 1..6
@@ -63,6 +67,12 @@ def main():
         for v in (512, 513):
             ms = timeit(lambda: call("rtdf_conv1d_ln_gelu_bf16", P(x), B, Lin, k, 2, P(w), P(v1), P(v1), P(v1), 1e-5, P(y), v, stream()), iters=5)
             print(f"conv{i + 1} L_out={Lout:5d} k={k} variant {v}: {ms:7.3f} ms  {2.0 * B * Lout * 512 * 512 * k / ms / 1e9:8.1f} TFLOP/s")
+        if i < 2:
+            for gv, gname in ((4, "hw-tanh"), (5, "A&S erf")):
+                call("rtdf_debug_gelu_variant", gv)
+                ms = timeit(lambda: call("rtdf_conv1d_ln_gelu_bf16", P(x), B, Lin, k, 2, P(w), P(v1), P(v1), P(v1), 1e-5, P(y), 512, stream()), iters=5)
+                print(f"conv{i + 1} L_out={Lout:5d} k={k} variant 512 gelu={gname}: {ms:7.3f} ms  {2.0 * B * Lout * 512 * 512 * k / ms / 1e9:8.1f} TFLOP/s")
+            call("rtdf_debug_gelu_variant", 0)
     # conv0
     wav = torch.randn(B, 64000, device=DEV)
     wt = torch.randn(10, 512, device=DEV)

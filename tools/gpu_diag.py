@@ -20,6 +20,7 @@ CHECKS = [
     ("gemm_bf16_v256", "tests.kernel_checks", "check_gemm_bf16", {"variants": (256,)}),
     ("gemm_bf16_v128", "tests.kernel_checks", "check_gemm_bf16", {"variants": (128,)}),
     ("gemm_bf16_v64", "tests.kernel_checks", "check_gemm_bf16", {"variants": (64,)}),
+    ("gelu_epilogue", "tests.kernel_checks", "check_gelu_epilogue", {}),
     ("conv1d_tc_v512", "tests.kernel_checks", "check_conv1d_tc", {"variants": (512,)}),
     ("conv1d_tc_v513", "tests.kernel_checks", "check_conv1d_tc", {"variants": (513,)}),
     ("posconv", "tests.kernel_checks", "check_posconv", {}),

@@ -52,6 +52,8 @@ typedef struct rtdf_model_desc {
   int conf_kernel;    /* Conformer: depth-wise conv kernel size (31)                */
   int conf_blocks;    /* Conformer: n_encoders (4)                                  */
   int attention_impl; /* 0 = tcgen05 tile kernel, 1 = SIMT kernel (debug)           */
+  int aasist_conv_impl; /* bf16 mode, residual-block + attention-map convs: 0 = tcgen05 with (hi,lo) bf16 operand
+                         * pairs, 3 MMAs per product (~fp32 accuracy); 1 = tcgen05 plain bf16; 2 = fp32 SIMT */
 } rtdf_model_desc;
 
 /* Optional intermediate outputs of a forward call (device pointers, may be NULL). */
@@ -119,6 +121,20 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
 /* GraphPool (aasist_modules.py:306-338) on h (B,n,D): out (B,k,D), idx (B,k) descending score. */
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream);
+
+/* Shifted-row tcgen05 convolution on zero-padded channels-last planes (bf16-mode AASIST residual encoder and
+ * attention map; replaces the cuDNN convs behind models/aasist_modules.py:340-397, models/xlsr_aasist.py:103).
+ * Planes: row m = (b*hp + y)*wp + x holds the channels of one pixel; x = 0 / wp-1 and unused y rows are zero.
+ * in_hi/in_lo: (rows, ci) bf16 operand pair (lo = v - hi; in_lo/w_lo may be NULL when nsplit == 1);
+ * w_hi/w_lo: [n_chunks][co][min(ci,64)]; chunk c multiplies the plane shifted by shift[c] rows, channel block
+ * sub[c].  Epilogue: v = acc + bias; v = v*s1 + t1; act1; v += resid; v = v*s2 + t2; act2 (act: 0 none, 3 SELU);
+ * rows with y outside [hp_lo, hp_hi] or x in {0, wp-1} are written as zero.  nsplit: 3 = hi*hi + lo*hi + hi*lo
+ * (~fp32 accuracy), 1 = plain bf16. */
+int rtdf_conv_planes_tc(const void* in_hi, const void* in_lo, int ci, long long rows, int hp, int wp,
+                        const void* w_hi, const void* w_lo, int co, int n_chunks, const int* shift, const int* sub,
+                        int hp_lo, int hp_hi, const float* bias, const float* s1, const float* t1, int act1,
+                        const float* resid, const float* s2, const float* t2, int act2, float* out_f32,
+                        void* out_hi, void* out_lo, int nsplit, void* stream);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Total number of kernels this library has launched in the calling process. */

@@ -3,6 +3,7 @@
 #include "../../include/rtdf.h"
 #include "aasist.cuh"
 #include "attention.cuh"
+#include "conv_tc.cuh"
 #include "frontend.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -133,6 +134,36 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
   }
   RTDF_REQUIRE(impl == 1, "rtdf_attention: the tcgen05 kernel takes bf16 inputs");
   return attention_simt_f32(s, static_cast<const float*>(qkv), static_cast<float*>(ctx_out), batch, n_frames, heads);
+}
+
+int rtdf_conv_planes_tc(const void* in_hi, const void* in_lo, int ci, long long rows, int hp, int wp,
+                        const void* w_hi, const void* w_lo, int co, int n_chunks, const int* shift, const int* sub,
+                        int hp_lo, int hp_hi, const float* bias, const float* s1, const float* t1, int act1,
+                        const float* resid, const float* s2, const float* t2, int act2, float* out_f32,
+                        void* out_hi, void* out_lo, int nsplit, void* stream) {
+  RTDF_REQUIRE(shift && n_chunks >= 1 && n_chunks <= kConvTcMaxChunks, "rtdf_conv_planes_tc: bad chunk table");
+  ConvTcArgs a;
+  a.in_hi = static_cast<const bf16*>(in_hi);
+  a.in_lo = static_cast<const bf16*>(in_lo);
+  a.ci = ci;
+  a.rows = rows;
+  a.Hp = hp;
+  a.Wp = wp;
+  a.w_hi = static_cast<const bf16*>(w_hi);
+  a.w_lo = static_cast<const bf16*>(w_lo);
+  a.co = co;
+  a.n_chunks = n_chunks;
+  for (int c = 0; c < n_chunks; ++c) {
+    a.shift[c] = shift[c];
+    a.sub[c] = sub ? sub[c] : 0;
+  }
+  a.hp_lo = hp_lo;
+  a.hp_hi = hp_hi;
+  a.bias = bias; a.s1 = s1; a.t1 = t1; a.act1 = act1; a.resid = resid; a.s2 = s2; a.t2 = t2; a.act2 = act2;
+  a.out_f32 = out_f32;
+  a.out_hi = static_cast<bf16*>(out_hi);
+  a.out_lo = static_cast<bf16*>(out_lo);
+  return conv_tc(static_cast<cudaStream_t>(stream), a, nsplit);
 }
 
 long long rtdf_launch_count(void) { return launch_count(); }

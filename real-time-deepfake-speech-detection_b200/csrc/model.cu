@@ -3,6 +3,7 @@
 
 #include "attention.cuh"
 #include "conformer.cuh"
+#include "conv_tc.cuh"
 #include "frontend.cuh"
 #include "gemm_simt.cuh"
 
@@ -241,6 +242,40 @@ static int pack_pool(rtdf_ctx* c, const std::string& p, int d, PoolW* w) {
   return RTDF_OK;
 }
 
+static bool aasist_tc(const rtdf_ctx* c) {
+  return c->d.precision == RTDF_PREC_BF16 && c->d.aasist_conv_impl != 2;
+}
+
+// (hi, lo) bf16 chunks [n_chunks][co][kw] of a conv / linear weight for the shifted-row tcgen05 kernel
+static int pack_tc_conv(rtdf_ctx* c, const float* src, int co, int ci, int taps /*KH*3, or 0 = linear*/, TcConvW* out) {
+  const int kw = ci < 64 ? ci : 64;
+  long long off[kConvTcMaxChunks];
+  long long stride_o, stride_k;
+  int n_chunks;
+  if (taps > 0) {          // conv weight [co][ci][kh][3]: chunk = tap, k = input channel
+    RTDF_REQUIRE(ci <= 64, "pack_tc_conv: conv with more than 64 input channels");
+    n_chunks = taps;
+    stride_o = (long long)ci * taps;
+    stride_k = taps;
+    for (int t = 0; t < taps; ++t) off[t] = t;
+  } else {                 // linear weight [co][ci]: chunk = 64-channel block
+    n_chunks = (ci + 63) / 64;
+    stride_o = ci;
+    stride_k = 1;
+    for (int t = 0; t < n_chunks; ++t) off[t] = 64LL * t;
+  }
+  bf16 *hi, *lo;
+  RTDF_TRY(dalloc(c, (long long)n_chunks * co * kw, &hi));
+  RTDF_TRY(dalloc(c, (long long)n_chunks * co * kw, &lo));
+  RTDF_TRY(conv_tc_pack_weight(0, src, co, kw, n_chunks, stride_o, stride_k, off, hi, lo));
+  out->hi = hi;
+  out->lo = lo;
+  out->ci = ci;
+  out->co = co;
+  out->n_chunks = n_chunks;
+  return RTDF_OK;
+}
+
 static int pack_aasist(rtdf_ctx* c) {
   AasistW& a = c->aasist;
   RTDF_TRY(make_lin(c, "LL", 128, 1024, true, &a.LL));
@@ -262,6 +297,19 @@ static int pack_aasist(rtdf_ctx* c) {
       RTDF_TRY(get_ptr(c, p + ".conv_downsample.bias", &b.ds_b, b.co));
     }
     // bn1.* exists in the state dict but its output is discarded by the reference (aasist_modules.py:376-383)
+    if (aasist_tc(c)) {
+      const float* w;
+      RTDF_TRY(get_ptr(c, p + ".conv1.weight", &w, (long long)b.co * b.ci * 6));
+      if (i == 0) b.conv1_raw = w;
+      else RTDF_TRY(pack_tc_conv(c, w, b.co, b.ci, 6, &b.tc1));
+      RTDF_TRY(get_ptr(c, p + ".conv2.weight", &w, (long long)b.co * b.co * 6));
+      RTDF_TRY(pack_tc_conv(c, w, b.co, b.co, 6, &b.tc2));
+      if (b.ci != b.co) {
+        RTDF_TRY(get_ptr(c, p + ".conv_downsample.weight", &w, (long long)b.co * b.ci * 3));
+        if (i == 0) b.ds_raw = w;
+        else RTDF_TRY(pack_tc_conv(c, w, b.co, b.ci, 3, &b.tcd));
+      }
+    }
   }
   RTDF_TRY(make_bn(c, "first_bn1", 64, &a.first_bn1));
   RTDF_TRY(make_transposed(c, "attention.0.weight", 128, 64, &a.att_w1t));
@@ -269,6 +317,36 @@ static int pack_aasist(rtdf_ctx* c) {
   RTDF_TRY(make_bn(c, "attention.2", 128, &a.att_bn));
   RTDF_TRY(make_transposed(c, "attention.3.weight", 64, 128, &a.att_w2t));
   RTDF_TRY(get_ptr(c, "attention.3.bias", &a.att_b2, 64));
+  if (aasist_tc(c)) {
+    // attention: conv1x1(64->128) -> SELU -> BN -> conv1x1(128->64).  The eval BatchNorm (scale s, shift t) folds
+    // exactly into the second conv: W2' = W2 diag(s), b2' = b2 + W2 t.
+    const float *w1, *w2, *b2;
+    RTDF_TRY(get_ptr(c, "attention.0.weight", &w1, 128 * 64));
+    RTDF_TRY(get_ptr(c, "attention.3.weight", &w2, 64 * 128));
+    RTDF_TRY(get_ptr(c, "attention.3.bias", &b2, 64));
+    RTDF_TRY(pack_tc_conv(c, w1, 128, 64, 0, &a.att1));
+    RTDF_CHECK_CUDA(cudaDeviceSynchronize());
+    std::vector<float> hw2(64 * 128), hb2(64), hs(128), ht(128);
+    RTDF_CHECK_CUDA(cudaMemcpy(hw2.data(), w2, hw2.size() * 4, cudaMemcpyDeviceToHost));
+    RTDF_CHECK_CUDA(cudaMemcpy(hb2.data(), b2, hb2.size() * 4, cudaMemcpyDeviceToHost));
+    RTDF_CHECK_CUDA(cudaMemcpy(hs.data(), a.att_bn.g, 128 * 4, cudaMemcpyDeviceToHost));
+    RTDF_CHECK_CUDA(cudaMemcpy(ht.data(), a.att_bn.b, 128 * 4, cudaMemcpyDeviceToHost));
+    for (int o = 0; o < 64; ++o) {
+      double acc = hb2[o];
+      for (int j = 0; j < 128; ++j) {
+        acc += (double)hw2[o * 128 + j] * ht[j];
+        hw2[o * 128 + j] *= hs[j];
+      }
+      hb2[o] = (float)acc;
+    }
+    float *dw2, *db2;
+    RTDF_TRY(dalloc(c, 64 * 128, &dw2));
+    RTDF_TRY(dalloc(c, 64, &db2));
+    RTDF_CHECK_CUDA(cudaMemcpy(dw2, hw2.data(), hw2.size() * 4, cudaMemcpyHostToDevice));
+    RTDF_CHECK_CUDA(cudaMemcpy(db2, hb2.data(), hb2.size() * 4, cudaMemcpyHostToDevice));
+    RTDF_TRY(pack_tc_conv(c, dw2, 64, 128, 0, &a.att2));
+    a.att_b2_folded = db2;
+  }
   RTDF_TRY(get_ptr(c, "pos_S", &a.pos_S, 42 * 64));
   RTDF_TRY(get_ptr(c, "master1", &a.master1, 64));
   RTDF_TRY(get_ptr(c, "master2", &a.master2, 64));
@@ -403,18 +481,42 @@ struct AasistWs {
   float* z;         // (M,128)
   float* r[4];      // (B,64,43,Tp) rotating conv buffers
   float* wmap;
+  // tcgen05 path: zero-padded channels-last planes [B*Hp*Wp][C]
+  struct Plane { float* f; bf16* hi; bf16* lo; } pl[2];   // block input / output (64 ch)
+  bf16 *y_hi, *y_lo;                                       // conv1 output (64 ch)
+  float* idt;                                              // conv_downsample output (64 ch)
+  bf16 *hid_hi, *hid_lo;                                   // attention hidden (128 ch)
   float *eS, *eT, *gS, *gT, *oS, *oT;
   struct Br { float *hx, *hy, *ma, *pS, *pT, *hx2, *hy2, *mb; } br[2];
   int *idxS, *idxT;
 };
+
+constexpr int kAasistHp = 44;   // plane rows per utterance: hp = h + 1 for 42-row tensors, hp = h for conv1's 43 rows
 
 static void plan_aasist(const rtdf_ctx* c, int B, int T, Bump& b, AasistWs* w) {
   const int Tp = T / 3, kT = Tp / 2 > 0 ? Tp / 2 : 1, kT2 = kT / 2 > 0 ? kT / 2 : 1;
   const long long M = (long long)B * T;
   w->featsb = c->d.precision == RTDF_PREC_BF16 ? (void*)b.take<bf16>(M * 1024) : nullptr;
   w->z = b.take<float>(M * 128);
-  for (int i = 0; i < 4; ++i) w->r[i] = b.take<float>((long long)B * 64 * 43 * Tp);
-  w->wmap = b.take<float>((long long)B * 64 * 42 * Tp);
+  if (aasist_tc(c)) {
+    const long long rows = (long long)B * kAasistHp * (Tp + 2);
+    w->r[0] = b.take<float>((long long)B * 42 * Tp);      // stem output, one channel
+    w->r[1] = w->r[2] = w->r[3] = nullptr;
+    for (int i = 0; i < 2; ++i) {
+      w->pl[i].f = b.take<float>(rows * 64);
+      w->pl[i].hi = b.take<bf16>(rows * 64);
+      w->pl[i].lo = b.take<bf16>(rows * 64);
+    }
+    w->y_hi = b.take<bf16>(rows * 64);
+    w->y_lo = b.take<bf16>(rows * 64);
+    w->idt = b.take<float>(rows * 64);
+    w->hid_hi = b.take<bf16>(rows * 128);
+    w->hid_lo = b.take<bf16>(rows * 128);
+    w->wmap = b.take<float>(rows * 64);
+  } else {
+    for (int i = 0; i < 4; ++i) w->r[i] = b.take<float>((long long)B * 64 * 43 * Tp);
+    w->wmap = b.take<float>((long long)B * 64 * 42 * Tp);
+  }
   w->eS = b.take<float>((long long)B * 42 * 64);
   w->eT = b.take<float>((long long)B * Tp * 64);
   w->gS = b.take<float>((long long)B * 42 * 64);
@@ -623,26 +725,8 @@ static GraphView view(const float* p, int n, long long bs) {
   return g;
 }
 
-static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, int T, const AasistWs& w, float* logits,
-                      const rtdf_taps* taps) {
+static int run_aasist_encoder_simt(rtdf_ctx* c, cudaStream_t s, int B, int Tp, const AasistWs& w) {
   const AasistW& a = c->aasist;
-  const bool bf = c->d.precision == RTDF_PREC_BF16;
-  const long long M = (long long)B * T;
-  const int Tp = T / 3, kT = Tp / 2 > 0 ? Tp / 2 : 1, kT2 = kT / 2 > 0 ? kT / 2 : 1;
-  RTDF_REQUIRE(Tp >= 1 && Tp <= 96, "AASIST back-end supports 3..290 frames, got T = %d", T);
-  {
-    TcEpilogue e;
-    e.bias = a.LL.b;
-    e.out_f32 = w.z;
-    e.ld_f32 = 128;
-    const void* A = feats;
-    if (bf) {
-      RTDF_TRY(cast_f32_to_bf16(s, feats, static_cast<bf16*>(w.featsb), M * 1024));
-      A = w.featsb;
-    }
-    RTDF_TRY(linear(c, s, A, M, a.LL, e));
-  }
-  RTDF_TRY(aasist_stem(s, w.z, B, T, a.first_bn_s, a.first_bn_t, w.r[0]));
   int cur = 0;
   for (int i = 0; i < 6; ++i) {
     const ResBlockW& b = a.blocks[i];
@@ -669,6 +753,107 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
   const float* x = w.r[cur];
   RTDF_TRY(aasist_attn_map(s, x, B, 42, Tp, a.att_w1t, a.att_b1, a.att_bn.g, a.att_bn.b, a.att_w2t, a.att_b2, w.wmap));
   RTDF_TRY(aasist_attn_pool(s, x, w.wmap, B, 42, Tp, a.pos_S, w.eS, w.eT));
+  return RTDF_OK;
+}
+
+// Residual encoder + attention map + attention pooling on zero-padded channels-last planes with the shifted-row
+// tcgen05 conv (conv_tc.cuh).  Plane conventions: 42-row tensors sit at hp = h + 1, conv1's 43-row output at hp = h.
+static int run_aasist_encoder_tc(rtdf_ctx* c, cudaStream_t s, int B, int Tp, const AasistWs& w) {
+  const AasistW& a = c->aasist;
+  const int Hp = kAasistHp, Wp = Tp + 2;
+  const long long rows = (long long)B * Hp * Wp;
+  const int nsplit = c->d.aasist_conv_impl == 1 ? 1 : 3;
+  auto base = [&](const TcConvW& wt) {
+    ConvTcArgs g;
+    g.rows = rows; g.Hp = Hp; g.Wp = Wp;
+    g.w_hi = wt.hi; g.w_lo = wt.lo; g.ci = wt.ci; g.co = wt.co; g.n_chunks = wt.n_chunks;
+    return g;
+  };
+  // conv1: (2,3) pad (1,1), 43 output rows at hp = h: input row hp + kh.  conv2: (2,3) pad (0,1), output at hp = h + 1:
+  // input row hp - 1 + kh.  downsample: (1,3) pad (0,1), same row.
+  auto taps_conv1 = [&](ConvTcArgs& g) { for (int kh = 0; kh < 2; ++kh) for (int kw = 0; kw < 3; ++kw) g.shift[kh * 3 + kw] = kh * Wp + kw - 1; g.hp_lo = 0; g.hp_hi = 42; };
+  auto taps_conv2 = [&](ConvTcArgs& g) { for (int kh = 0; kh < 2; ++kh) for (int kw = 0; kw < 3; ++kw) g.shift[kh * 3 + kw] = (kh - 1) * Wp + kw - 1; g.hp_lo = 1; g.hp_hi = 42; };
+  auto taps_ds = [&](ConvTcArgs& g) { for (int kw = 0; kw < 3; ++kw) g.shift[kw] = kw - 1; g.hp_lo = 1; g.hp_hi = 42; };
+  int cur = 0;
+  for (int i = 0; i < 6; ++i) {
+    const ResBlockW& b = a.blocks[i];
+    const AasistWs::Plane& X = w.pl[cur];
+    const AasistWs::Plane& O = w.pl[cur ^ 1];
+    const float* resid = X.f;
+    if (i == 0) {
+      RTDF_TRY(conv_tc_block0(s, w.r[0], B, Tp, Hp, Wp, b.conv1_raw, b.conv1_b, b.bn2.g, b.bn2.b, b.ds_raw, b.ds_b,
+                              w.y_hi, w.y_lo, w.idt));
+      resid = w.idt;
+    } else {
+      ConvTcArgs c1 = base(b.tc1);
+      taps_conv1(c1);
+      c1.in_hi = X.hi; c1.in_lo = X.lo;
+      c1.bias = b.conv1_b; c1.s1 = b.bn2.g; c1.t1 = b.bn2.b; c1.act1 = ACT_SELU;
+      c1.out_hi = w.y_hi; c1.out_lo = w.y_lo;
+      RTDF_TRY(conv_tc(s, c1, nsplit));
+      if (b.tcd.hi) {
+        ConvTcArgs cd = base(b.tcd);
+        taps_ds(cd);
+        cd.in_hi = X.hi; cd.in_lo = X.lo;
+        cd.bias = b.ds_b;
+        cd.out_f32 = w.idt;
+        RTDF_TRY(conv_tc(s, cd, nsplit));
+        resid = w.idt;
+      }
+    }
+    ConvTcArgs c2 = base(b.tc2);
+    taps_conv2(c2);
+    c2.in_hi = w.y_hi; c2.in_lo = w.y_lo;
+    c2.bias = b.conv2_b; c2.resid = resid;
+    if (i == 5) { c2.s2 = a.first_bn1.g; c2.t2 = a.first_bn1.b; c2.act2 = ACT_SELU; }   // xlsr_aasist.py:100-101
+    c2.out_f32 = O.f; c2.out_hi = O.hi; c2.out_lo = O.lo;
+    RTDF_TRY(conv_tc(s, c2, nsplit));
+    cur ^= 1;
+  }
+  const AasistWs::Plane& X = w.pl[cur];
+  {
+    ConvTcArgs g1 = base(a.att1);
+    g1.hp_lo = 1; g1.hp_hi = 42;
+    g1.in_hi = X.hi; g1.in_lo = X.lo;
+    g1.bias = a.att_b1; g1.act1 = ACT_SELU;
+    g1.out_hi = w.hid_hi; g1.out_lo = w.hid_lo;
+    RTDF_TRY(conv_tc(s, g1, nsplit));
+    ConvTcArgs g2 = base(a.att2);
+    g2.hp_lo = 1; g2.hp_hi = 42;
+    g2.sub[0] = 0; g2.sub[1] = 1;
+    g2.in_hi = w.hid_hi; g2.in_lo = w.hid_lo;
+    g2.bias = a.att_b2_folded;
+    g2.out_f32 = w.wmap;
+    RTDF_TRY(conv_tc(s, g2, nsplit));
+  }
+  return attn_pool_planes(s, X.f, w.wmap, B, 42, Tp, Hp, Wp, a.pos_S, w.eS, w.eT);
+}
+
+static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, int T, const AasistWs& w, float* logits,
+                      const rtdf_taps* taps) {
+  const AasistW& a = c->aasist;
+  const bool bf = c->d.precision == RTDF_PREC_BF16;
+  const long long M = (long long)B * T;
+  const int Tp = T / 3, kT = Tp / 2 > 0 ? Tp / 2 : 1, kT2 = kT / 2 > 0 ? kT / 2 : 1;
+  RTDF_REQUIRE(Tp >= 1 && Tp <= 96, "AASIST back-end supports 3..290 frames, got T = %d", T);
+  {
+    TcEpilogue e;
+    e.bias = a.LL.b;
+    e.out_f32 = w.z;
+    e.ld_f32 = 128;
+    const void* A = feats;
+    if (bf) {
+      RTDF_TRY(cast_f32_to_bf16(s, feats, static_cast<bf16*>(w.featsb), M * 1024));
+      A = w.featsb;
+    }
+    RTDF_TRY(linear(c, s, A, M, a.LL, e));
+  }
+  RTDF_TRY(aasist_stem(s, w.z, B, T, a.first_bn_s, a.first_bn_t, w.r[0]));
+  if (aasist_tc(c)) {
+    RTDF_TRY(run_aasist_encoder_tc(c, s, B, Tp, w));
+  } else {
+    RTDF_TRY(run_aasist_encoder_simt(c, s, B, Tp, w));
+  }
   RTDF_TRY(aasist_gat_rows(s, 64, 64, view(w.eS, 42, 42 * 64), B, 42, a.gat_S, w.gS, 42 * 64, nullptr, 0, nullptr, nullptr));
   RTDF_TRY(aasist_gat_rows(s, 64, 64, view(w.eT, Tp, (long long)Tp * 64), B, Tp, a.gat_T, w.gT, (long long)Tp * 64, nullptr, 0, nullptr, nullptr));
   RTDF_TRY(aasist_graph_pool(s, 64, view(w.gS, 42, 42 * 64), B, a.pool_S.w, a.pool_S.b, 21, w.oS, w.idxS));

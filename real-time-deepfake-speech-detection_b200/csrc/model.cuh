@@ -40,8 +40,16 @@ struct XlsrLayer {
   Norm ln1, ln2;
 };
 
+struct TcConvW {      // weights of one shifted-row tcgen05 conv: [n_chunks][co][min(ci,64)] bf16 (hi, lo)
+  const bf16* hi = nullptr;
+  const bf16* lo = nullptr;
+  int ci = 0, co = 0, n_chunks = 0;
+};
+
 struct ResBlockW {
   const float* conv1_w = nullptr; const float* conv1_b = nullptr;
+  const float* conv1_raw = nullptr; const float* ds_raw = nullptr;   // state-dict layout [co][ci][kh][3] (block 0)
+  TcConvW tc1, tc2, tcd;
   Norm bn2;
   const float* conv2_w = nullptr; const float* conv2_b = nullptr;
   const float* ds_w = nullptr; const float* ds_b = nullptr;
@@ -64,6 +72,8 @@ struct AasistW {
   Norm first_bn1;
   const float* att_w1t = nullptr; const float* att_b1 = nullptr; Norm att_bn;
   const float* att_w2t = nullptr; const float* att_b2 = nullptr;
+  TcConvW att1, att2;                      // attention 1x1 convs; eval BatchNorm folded into att2 / att_b2_folded
+  const float* att_b2_folded = nullptr;
   const float* pos_S = nullptr; const float* master1 = nullptr; const float* master2 = nullptr;
   GatRowWeights gat_S, gat_T;
   HsGalW st11, st12, st21, st22;

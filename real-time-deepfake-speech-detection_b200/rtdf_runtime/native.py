@@ -19,7 +19,8 @@ ACT_NONE, ACT_GELU, ACT_SWISH, ACT_SELU = 0, 1, 2, 3
 
 class ModelDesc(ctypes.Structure):
     _fields_ = [("backend", c_int), ("n_layers", c_int), ("precision", c_int), ("conf_emb", c_int),
-                ("conf_heads", c_int), ("conf_kernel", c_int), ("conf_blocks", c_int), ("attention_impl", c_int)]
+                ("conf_heads", c_int), ("conf_kernel", c_int), ("conf_blocks", c_int), ("attention_impl", c_int),
+                ("aasist_conv_impl", c_int)]
 
 
 class Taps(ctypes.Structure):
@@ -49,6 +50,10 @@ SIGNATURES = {
     "rtdf_posconv_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_posconv_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rtdf_conv_planes_tc": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                    ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_void_p]),
     "rtdf_launch_count": (c_longlong, []),
     "rtdf_debug_gelu_variant": (c_int, [c_int]),
     "rtdf_profile_begin": (c_int, []),

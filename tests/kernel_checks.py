@@ -172,6 +172,87 @@ def check_gelu_epilogue():
     return out
 
 
+def _split(t):
+    hi = t.to(torch.bfloat16)
+    return hi, (t - hi.float()).to(torch.bfloat16)
+
+
+def check_conv_planes_tc(nsplit=3):
+    """Shifted-row tcgen05 conv on zero-padded channels-last planes against F.conv2d (fp32) for the three
+    Residual_block convolutions (aasist_modules.py:340-397) and the 1x1 attention convs (xlsr_aasist.py:103)."""
+    import ctypes
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    Hp = 44
+    cases = [  # (kind, ci, co, B, W)
+        ("conv1", 32, 32, 2, 16), ("conv1", 32, 64, 1, 66), ("conv1", 64, 64, 2, 66), ("conv2", 32, 32, 2, 66),
+        ("conv2", 64, 64, 3, 67), ("ds", 32, 64, 2, 66), ("lin", 64, 128, 2, 66), ("lin", 128, 64, 2, 16),
+        ("conv2", 64, 64, 1, 96),
+    ]
+    for kind, ci, co, B, W in cases:
+        Wp = W + 2
+        rows = B * Hp * Wp
+        Hin = 43 if kind == "conv2" else 42
+        x = torch.randn(B, ci, Hin, W, generator=g)
+        plane = torch.zeros(B, Hp, Wp, ci)
+        r0 = 0 if kind == "conv2" else 1            # 43-row tensors sit at hp = h, 42-row tensors at hp = h + 1
+        plane[:, r0:r0 + Hin, 1:W + 1, :] = x.permute(0, 2, 3, 1)
+        bias = torch.randn(co, generator=g) * 0.1
+        s1 = 1 + 0.1 * torch.randn(co, generator=g)
+        t1 = 0.1 * torch.randn(co, generator=g)
+        s2 = 1 + 0.1 * torch.randn(co, generator=g)
+        t2 = 0.1 * torch.randn(co, generator=g)
+        if kind == "lin":
+            w = torch.randn(co, ci, generator=g) / math.sqrt(ci)
+            ref = F.conv2d(x, w[:, :, None, None], bias)
+            nb = (ci + 63) // 64
+            wch = torch.stack([w[:, 64 * j:64 * j + min(ci, 64)] for j in range(nb)])           # [chunk][co][kw]
+            shift, sub, h0, nrow = [0] * nb, list(range(nb)), 1, 42
+            hp_lo, hp_hi = 1, 42
+        else:
+            KH = 1 if kind == "ds" else 2
+            w = torch.randn(co, ci, KH, 3, generator=g) / math.sqrt(ci * KH * 3)
+            pad_h = 1 if kind == "conv1" else 0
+            ref = F.conv2d(x, w, bias, padding=(pad_h, 1))
+            wch = torch.stack([w[:, :, kh, kw] for kh in range(KH) for kw in range(3)])          # [tap][co][ci]
+            if kind == "conv1":
+                shift = [kh * Wp + kw - 1 for kh in range(2) for kw in range(3)]
+                h0, nrow, hp_lo, hp_hi = 0, 43, 0, 42
+            elif kind == "conv2":
+                shift = [(kh - 1) * Wp + kw - 1 for kh in range(2) for kw in range(3)]
+                h0, nrow, hp_lo, hp_hi = 1, 42, 1, 42
+            else:
+                shift = [kw - 1 for kw in range(3)]
+                h0, nrow, hp_lo, hp_hi = 1, 42, 1, 42
+            sub = [0] * len(shift)
+        resid = torch.zeros(B, Hp, Wp, co)
+        resid[:, h0:h0 + nrow, 1:W + 1, :] = torch.randn(B, nrow, W, co, generator=g)
+        expect = F.selu(ref * s1[None, :, None, None] + t1[None, :, None, None])
+        expect = expect.permute(0, 2, 3, 1) + resid[:, h0:h0 + nrow, 1:W + 1, :]
+        expect = F.selu(expect * s2 + t2)
+        full = torch.zeros(B, Hp, Wp, co)
+        full[:, h0:h0 + nrow, 1:W + 1, :] = expect
+        xh, xl = _split(plane.reshape(rows, ci))
+        wh, wl = _split(wch.contiguous())
+        o32 = torch.full((rows, co), float("nan"), device=DEV)
+        oh = torch.empty(rows, co, dtype=torch.bfloat16, device=DEV)
+        ol = torch.empty(rows, co, dtype=torch.bfloat16, device=DEV)
+        n = len(shift)
+        sh = (ctypes.c_int * n)(*shift)
+        sb = (ctypes.c_int * n)(*sub)
+        call("rtdf_conv_planes_tc", P(dev(xh)), P(dev(xl)), ci, rows, Hp, Wp, P(dev(wh)), P(dev(wl)), co, n, sh, sb,
+             hp_lo, hp_hi, P(dev(bias)), P(dev(s1)), P(dev(t1)), 3, P(dev(resid.reshape(rows, co))), P(dev(s2)),
+             P(dev(t2)), 3, P(o32), P(oh), P(ol), nsplit, stream())
+        got = o32.cpu().reshape(B, Hp, Wp, co)
+        d = float((got - full).abs().max())
+        d16 = float(((oh.float() + ol.float()).cpu().reshape(B, Hp, Wp, co) - full).abs().max())
+        out[f"{kind}_{ci}to{co}_B{B}_W{W}"] = (d, d16)
+        assert torch.isfinite(got).all(), out
+        assert d <= (2e-4 if nsplit == 3 else 5e-2), out     # 3-term split: ~2^-16 relative per product
+        assert d16 <= d + 1e-4, out                           # hi + lo reproduces the fp32 plane to ~2^-17
+    return out
+
+
 def _conv_ref(x, w, b, gamma, beta, stride):
     y = F.conv1d(x.transpose(1, 2), w, b, stride=stride)             # (B,512,L)
     return F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))

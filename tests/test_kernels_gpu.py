@@ -46,6 +46,11 @@ def test_conv1d_implicit_gemm_ln_gelu(variant):
     kc.check_conv1d_tc(variants=(variant,))
 
 
+@pytest.mark.parametrize("nsplit", [3, 1])
+def test_conv_planes_tcgen05(nsplit):
+    kc.check_conv_planes_tc(nsplit=nsplit)
+
+
 def test_posconv():
     kc.check_posconv()
 

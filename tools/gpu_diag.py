@@ -23,6 +23,8 @@ CHECKS = [
     ("gelu_epilogue", "tests.kernel_checks", "check_gelu_epilogue", {}),
     ("conv1d_tc_v512", "tests.kernel_checks", "check_conv1d_tc", {"variants": (512,)}),
     ("conv1d_tc_v513", "tests.kernel_checks", "check_conv1d_tc", {"variants": (513,)}),
+    ("conv_planes_tc_x3", "tests.kernel_checks", "check_conv_planes_tc", {"nsplit": 3}),
+    ("conv_planes_tc_x1", "tests.kernel_checks", "check_conv_planes_tc", {"nsplit": 1}),
     ("posconv", "tests.kernel_checks", "check_posconv", {}),
     ("attention_simt", "tests.kernel_checks", "check_attention", {"impls": (1,)}),
     ("attention_tc", "tests.kernel_checks", "check_attention", {"impls": (0,)}),

@@ -51,7 +51,7 @@ typedef struct rtdf_model_desc {
   int conf_heads;     /* Conformer: heads (4)                                       */
   int conf_kernel;    /* Conformer: depth-wise conv kernel size (31)                */
   int conf_blocks;    /* Conformer: n_encoders (4)                                  */
-  int attention_impl; /* 0 = tcgen05 tile kernel, 1 = SIMT kernel (debug)           */
+  int attention_impl; /* 0 = tcgen05 warp-specialised kernel, 1 = SIMT (debug), 2 = tcgen05 tile kernel (A/B) */
   int aasist_conv_impl; /* bf16 mode, residual-block + attention-map convs: 0 = tcgen05 with (hi,lo) bf16 operand
                          * pairs, 3 MMAs per product (~fp32 accuracy); 1 = tcgen05 plain bf16; 2 = fp32 SIMT */
 } rtdf_model_desc;
@@ -115,7 +115,8 @@ int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames,
                       const float* bias, void* stream);
 int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const float* w_packed, const float* bias,
                      void* stream);
-/* qkv (B*T, 3*H*64) [q|k|v] with q pre-scaled -> ctx (B*T, H*64).  impl 0 = tcgen05, 1 = SIMT. */
+/* qkv (B*T, 3*H*64) [q|k|v] with q pre-scaled -> ctx (B*T, H*64).  impl 0 = tcgen05 warp-specialised (P in
+ * tensor memory), 1 = SIMT, 2 = tcgen05 one-tile-per-CTA kernel. */
 int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int heads, int is_bf16, int impl,
                    void* stream);
 /* GraphPool (aasist_modules.py:306-338) on h (B,n,D): out (B,k,D), idx (B,k) descending score. */

@@ -129,7 +129,8 @@ int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int 
                    void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (is_bf16) {
-    if (impl == 0) return attention_tc(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
+    if (impl == 0) return attention_ws(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
+    if (impl == 2) return attention_tc(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
     return attention_simt_bf16(s, static_cast<const bf16*>(qkv), static_cast<bf16*>(ctx_out), batch, n_frames, heads);
   }
   RTDF_REQUIRE(impl == 1, "rtdf_attention: the tcgen05 kernel takes bf16 inputs");

@@ -168,6 +168,246 @@ int attention_tc(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
 }
 
 // =================================================================================================
+// Warp-specialised persistent kernel (default).  One CTA per SM loops over (utterance, head, 128-query tile):
+//   warp 0      : TMA producer, ring of stages {Q 128x64 | K Tk x 64 | V Tk x 64} (SWIZZLE_128B)
+//   warp 1      : single-thread tcgen05.mma issuer:  S = Q K^T (SS form) into TMEM buffer g = item & 1, and
+//                 O = P V with P read from TENSOR MEMORY (TS form) and V as MN-major B operand
+//   warps 2..5 / 6..9 : two softmax warpgroups, one per TMEM buffer (ping-pong): row max, exp2, bf16 probabilities
+//                 written back over the S columns with tcgen05.st (P never touches shared memory), O / rowsum -> ctx
+// TMEM buffer g (256 columns): S fp32 [0, Tk) ; P bf16x2 [0, Tk/2) (in place) ; O fp32 [128, 192).
+// S(i+1) is issued before PV(i), so both warpgroups' softmax passes and the tensor pipe overlap.
+// =================================================================================================
+constexpr int kWsThreads = 320;
+constexpr int kWsMaxStages = 6;
+
+struct AttWsParams {
+  int T, H, Tk, n_qt, total_items, n_stages, stage_bytes, kv_bytes;
+};
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
+                    bf16* __restrict__ ctx, const AttWsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + p.n_stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kWsMaxStages + s); };
+  auto sfull_bar = [&](int g) { return bars + 8u * (2 * kWsMaxStages + g); };
+  auto pfull_bar = [&](int g) { return bars + 8u * (2 * kWsMaxStages + 2 + g); };
+  auto ofull_bar = [&](int g) { return bars + 8u * (2 * kWsMaxStages + 4 + g); };
+  auto tempty_bar = [&](int g) { return bars + 8u * (2 * kWsMaxStages + 6 + g); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kWsMaxStages + 8);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + p.n_stages * p.stage_bytes + 8 * (2 * kWsMaxStages + 8));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&mapQ);
+    prefetch_tmap(&mapKV);
+    for (int s = 0; s < kWsMaxStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(sfull_bar(g), 1);
+      mbar_init(pfull_bar(g), 128);
+      mbar_init(ofull_bar(g), 1);
+      mbar_init(tempty_bar(g), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int HD = p.H * 64;
+  const int n_local = p.total_items > (int)blockIdx.x ? (p.total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int i = 0; i < n_local; ++i) {
+        const int item = blockIdx.x + i * gridDim.x;
+        const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+        const int s = i % p.n_stages;
+        const uint32_t ph = (i / p.n_stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), 16384u + 2u * p.kv_bytes);
+        const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384, sV = sK + p.kv_bytes;
+        tma_load_3d(sQ, &mapQ, full_bar(s), h * 64, qt * 128, b);
+        tma_load_3d(sK, &mapKV, full_bar(s), HD + h * 64, 0, b);
+        tma_load_3d(sV, &mapKV, full_bar(s), 2 * HD + h * 64, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.Tk);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64, /*a_mn=*/0, /*b_mn=*/1);
+      const int ksteps = p.Tk / 16;
+      auto issue_pv = [&](int j) {
+        const int g = j & 1, s = j % p.n_stages;
+        mbar_wait(pfull_bar(g), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sV = base + s * p.stage_bytes + 16384 + p.kv_bytes;
+        const uint32_t tP = tmem + g * 256, tO = tmem + g * 256 + 128;
+        for (int ks = 0; ks < ksteps; ++ks)
+          mma_bf16_ts(tO, tP + ks * 8, umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
+        mma_commit(empty_bar(s));     // Q, K, V of this stage are no longer read
+        mma_commit(ofull_bar(g));
+      };
+      for (int i = 0; i < n_local; ++i) {
+        const int g = i & 1, s = i % p.n_stages;
+        mbar_wait(tempty_bar(g), ((i >> 1) & 1) ^ 1);   // warpgroup g has read O of item i - 2
+        mbar_wait(full_bar(s), (i / p.n_stages) & 1);
+        tc_fence_after();
+        const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_bf16_ss(tmem + g * 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+        mma_commit(sfull_bar(g));
+        if (i > 0) issue_pv(i - 1);
+      }
+      if (n_local > 0) issue_pv(n_local - 1);
+    }
+  } else {
+    // ===== softmax warpgroups =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;                      // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;                 // row inside the query tile
+    const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
+    const int nchunks = p.Tk / 16;
+    const int T = p.T;
+    const float kLog2e = 1.4426950408889634f;
+    for (int i = g; i < n_local; i += 2) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
+      const uint32_t ph = (i >> 1) & 1;
+      const bool warp_active = qt * 128 + q * 32 < T;        // warp-uniform: any valid query row in this warp
+      mbar_wait(sfull_bar(g), ph);
+      __syncwarp();
+      tc_fence_after();
+      float sum = 1.f;
+      if (warp_active) {
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c * 16, v);
+          tmem_ld_wait();
+          if (c * 16 + 16 <= T) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c * 16 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        }
+        const float mxs = mx * kLog2e;
+        sum = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c * 16, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+          const bool fullc = c * 16 + 16 <= T;      // warp-uniform
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mxs));
+            float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mxs));
+            if (!fullc) {
+              if (c * 16 + 2 * j >= T) e0 = 0.f;
+              if (c * 16 + 2 * j + 1 >= T) e1 = 0.f;
+            }
+            // accumulate the bf16-rounded probabilities so that numerator and denominator agree
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+            sum += __low2float(h2) + __high2float(h2);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          tmem_st8(t_row + c * 8, pk);          // P chunk c overwrites S columns [8c, 8c+8), already consumed
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(pfull_bar(g));
+      mbar_wait(ofull_bar(g), ph);
+      __syncwarp();
+      tc_fence_after();
+      if (warp_active) {
+        const float inv = 1.0f / sum;
+        const int tq = qt * 128 + r;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_row + 128, v0);
+        tmem_ld32(t_row + 160, v1);
+        tmem_ld_wait();
+        if (tq < T) {
+          bf16* dst = ctx + ((long long)b * T + tq) * HD + h * 64;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(
+                pack_bf16x2(__uint_as_float(v0[j]) * inv, __uint_as_float(v0[j + 1]) * inv),
+                pack_bf16x2(__uint_as_float(v0[j + 2]) * inv, __uint_as_float(v0[j + 3]) * inv),
+                pack_bf16x2(__uint_as_float(v0[j + 4]) * inv, __uint_as_float(v0[j + 5]) * inv),
+                pack_bf16x2(__uint_as_float(v0[j + 6]) * inv, __uint_as_float(v0[j + 7]) * inv));
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + 32 + j) = make_uint4(
+                pack_bf16x2(__uint_as_float(v1[j]) * inv, __uint_as_float(v1[j + 1]) * inv),
+                pack_bf16x2(__uint_as_float(v1[j + 2]) * inv, __uint_as_float(v1[j + 3]) * inv),
+                pack_bf16x2(__uint_as_float(v1[j + 4]) * inv, __uint_as_float(v1[j + 5]) * inv),
+                pack_bf16x2(__uint_as_float(v1[j + 6]) * inv, __uint_as_float(v1[j + 7]) * inv));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(g));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H) {
+  RTDF_REQUIRE(qkv && ctx && B > 0 && H > 0, "attention_ws: bad arguments");
+  RTDF_REQUIRE(T >= 1 && T <= 256, "attention_ws: T = %d frames unsupported (1..256; <= 5.1 s of audio)", T);
+  AttWsParams p;
+  p.T = T;
+  p.H = H;
+  p.Tk = (T + 15) & ~15;
+  p.n_qt = ceil_div(T, 128);
+  const long long items = (long long)B * H * p.n_qt;
+  RTDF_REQUIRE(items < (1LL << 30), "attention_ws: batch too large");
+  p.total_items = (int)items;
+  p.kv_bytes = p.Tk * 128;
+  p.stage_bytes = 16384 + 2 * p.kv_bytes;
+  const int budget = 232448 - 1024 - 256;
+  p.n_stages = budget / p.stage_bytes;
+  if (p.n_stages > kWsMaxStages) p.n_stages = kWsMaxStages;
+  RTDF_REQUIRE(p.n_stages >= 2, "attention_ws: stage of %d bytes does not fit twice", p.stage_bytes);
+  const size_t smem = (size_t)p.n_stages * p.stage_bytes + 256 + 1024;
+  CUtensorMap mapQ, mapKV;
+  uint64_t dims[3] = {(uint64_t)3 * H * 64, (uint64_t)T, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)3 * H * 64 * 2, (uint64_t)T * 3 * H * 64 * 2};
+  uint32_t boxq[3] = {64, 128, 1};
+  uint32_t boxkv[3] = {64, (uint32_t)p.Tk, 1};
+  RTDF_TRY(make_tmap_bf16(&mapQ, qkv, 3, dims, strides, boxq, TMAP_SW128));
+  RTDF_TRY(make_tmap_bf16(&mapKV, qkv, 3, dims, strides, boxkv, TMAP_SW128));
+  RTDF_CHECK_CUDA(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
+  attention_ws_kernel<<<grid, kWsThreads, smem, s>>>(mapQ, mapKV, ctx, p);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// =================================================================================================
 // SIMT kernel: K/V of one head staged in smem as fp32; one warp per query at a time.
 // =================================================================================================
 constexpr int kSimtQPerCta = 32;

@@ -8,7 +8,11 @@ namespace rtdf {
 // ctx: (B*T, H*64).  Softmax statistics in fp32.  Replaces fairseq MultiheadAttention's core
 // (bmm -> softmax -> bmm), reference models/fe.py:19.
 
-// tcgen05 path: one CTA per (query tile of 128, head, utterance): S = Q K^T in TMEM, fp32 softmax in
+// tcgen05 path (default): persistent warp-specialised kernel -- TMA producer warp, MMA issuer warp, two softmax
+// warpgroups ping-ponging over two TMEM buffers; S = Q K^T (SS), P written back to TMEM, O = P V (TS).
+int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H);
+
+// earlier tile kernel, kept for A/B runs: one CTA per (query tile of 128, head, utterance): S = Q K^T in TMEM, fp32 softmax in
 // registers, P (bf16) staged in swizzled smem, O = P V in TMEM.
 int attention_tc(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H);
 

@@ -675,6 +675,8 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     }
     if (bf) {
       if (c->d.attention_impl == 0)
+        RTDF_TRY(attention_ws(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
+      else if (c->d.attention_impl == 2)
         RTDF_TRY(attention_tc(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
       else
         RTDF_TRY(attention_simt_bf16(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));

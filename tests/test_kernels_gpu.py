@@ -55,7 +55,7 @@ def test_posconv():
     kc.check_posconv()
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention(impl):
     kc.check_attention(impls=(impl,))
 

@@ -89,7 +89,7 @@ def main():
     # attention
     qkv = torch.randn(M, 3072, device=DEV).to(bf)
     ctx = torch.empty(M, 1024, dtype=bf, device=DEV)
-    for impl in (0, 1):
+    for impl in (0, 2, 1):
         ms = timeit(lambda: call("rtdf_attention", P(qkv), P(ctx), B, T, 16, 1, impl, stream()), iters=5)
         print(f"attention impl {impl}: {ms:7.3f} ms  {4.0 * B * 16 * T * T * 64 / ms / 1e9:8.1f} TFLOP/s")
     # pos-conv

@@ -27,7 +27,8 @@ CHECKS = [
     ("conv_planes_tc_x1", "tests.kernel_checks", "check_conv_planes_tc", {"nsplit": 1}),
     ("posconv", "tests.kernel_checks", "check_posconv", {}),
     ("attention_simt", "tests.kernel_checks", "check_attention", {"impls": (1,)}),
-    ("attention_tc", "tests.kernel_checks", "check_attention", {"impls": (0,)}),
+    ("attention_ws", "tests.kernel_checks", "check_attention", {"impls": (0,)}),
+    ("attention_tile", "tests.kernel_checks", "check_attention", {"impls": (2,)}),
     ("graph_pool", "tests.kernel_checks", "check_graph_pool", {}),
     ("backend_block_fp32", "tests.e2e_checks", "check_backend_block", {"precision": "fp32"}),
     ("backend_block_bf16", "tests.e2e_checks", "check_backend_block", {"precision": "bf16"}),

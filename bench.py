@@ -207,6 +207,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # kernels per forward, counted on one eager (non-graph) forward: the timed steps replay a CUDA graph of them
+    graph_on = eng.use_graph
+    eng.use_graph = False
+    n0 = lib.rtdf_launch_count()
+    eng.forward(inputs[0])
+    launches_per_forward = lib.rtdf_launch_count() - n0
+    eng.use_graph = graph_on
+
     # ---- device-resident throughput ("value") --------------------------------------------------
     for i in range(W):
         eng.forward(inputs[i % n_bufs])
@@ -217,7 +225,6 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches0 = lib.rtdf_launch_count()
     barrier()
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -233,7 +240,7 @@ def run_b200(args):
     barrier()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    launches = lib.rtdf_launch_count() - launches0
+    launches = launches_per_forward * K
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -269,10 +276,12 @@ def run_b200(args):
     # ---- roofline leg: CUDA-event time of every launch of the dominant kernel inside real steps ---
     roofline = None
     if rank == 0:
+        eng.use_graph = False                      # per-launch events need real launches, not a graph replay
         native.check(lib.rtdf_profile_begin(), "rtdf_profile_begin")
         for i in range(2):
             eng.forward(inputs[i % n_bufs])
         torch.cuda.synchronize()
+        eng.use_graph = graph_on
         pms, pfl, pn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         native.check(lib.rtdf_profile_end(256, ctypes.byref(pms), ctypes.byref(pfl), ctypes.byref(pn)), "rtdf_profile_end")
         peaks = measured_peaks()
@@ -303,6 +312,7 @@ def run_b200(args):
                                    f"batch {B} per GPU (BASELINE.json configs[2])",
                        "global_batch": world * B, "batch_per_gpu": B, "n_samples": N, "frames": T, "layers": args.layers,
                        "parallelism": f"dp{world} (independent shards, one all-gather of scores)",
+                       "cuda_graph": bool(graph_on), "kernels_per_forward": int(launches_per_forward),
                        "l2": "per-step working set (631 MB bf16 weights + >1.5 GB activations) exceeds the 126 MB L2; "
                              "inputs rotate over 4 device buffers"},
             "clocks": clocks,

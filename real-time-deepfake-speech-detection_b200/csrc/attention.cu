@@ -224,6 +224,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot_gen;
   const int HD = p.H * 64;
   const int n_local = p.total_items > (int)blockIdx.x ? (p.total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -274,6 +275,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (i > 0) issue_pv(i - 1);
       }
       if (n_local > 0) issue_pv(n_local - 1);
+      pdl_launch_dependents();
     }
   } else {
     // ===== softmax warpgroups =====
@@ -402,7 +404,7 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   RTDF_TRY(make_tmap_bf16(&mapKV, qkv, 3, dims, strides, boxkv, TMAP_SW128));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
-  attention_ws_kernel<<<grid, kWsThreads, smem, s>>>(mapQ, mapKV, ctx, p);
+  RTDF_CHECK_CUDA(launch_pdl(attention_ws_kernel, dim3(grid), dim3(kWsThreads), smem, s, mapQ, mapKV, ctx, p));
   RTDF_LAUNCH_CHECK();
   return RTDF_OK;
 }

@@ -53,6 +53,35 @@ void count_launch();
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// Kernels of the per-layer chain are launched with the programmatic-stream-serialization attribute: their CTAs may
+// become resident and run their prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous
+// kernel drains; pdl_wait() then blocks until that kernel has completed and its writes are visible.  Every kernel
+// launched through launch_pdl() MUST call pdl_wait() before its first global-memory access that depends on (or
+// could overwrite the inputs of) the previous kernel.  Opt-in with RTDF_PDL=1 (it measured slower than plain stream
+// order inside the CUDA graph on B200, profiles/r01_notes.md).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 constexpr int kNumSMs = 148;  // B200
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

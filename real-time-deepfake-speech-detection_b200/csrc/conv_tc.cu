@@ -2,7 +2,7 @@
 //   warp 0      : TMA producer -- weights once per CTA, then one A slab (128 + span rows) per 128-row tile
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; per tile n_chunks x nsplit x KW/16 MMAs whose
 //                 A descriptors start (shift_c - shift_min) rows into the slab; double-buffered accumulators
-//   warps 2..5  : epilogue, one output row per thread: bias / folded BN / SELU / residual / second BN+SELU,
+//   warps 2..9  : epilogue, one output row and half of the columns per thread: bias / folded BN / SELU / residual / second BN+SELU,
 //                 zero at padding positions, fp32 plane + bf16 (hi, lo) planes
 #include "conv_tc.cuh"
 
@@ -20,8 +20,8 @@ namespace {
 constexpr int kMaxSmem = 232448;
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 4;
-constexpr int kThreads = 192;       // TMA warp, MMA warp, 4 epilogue warps
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;       // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 
 struct KParams {
   long long rows;
@@ -33,7 +33,6 @@ struct KParams {
   float* out_f32;
   bf16* out_hi;
   bf16* out_lo;
-  int desc_bo;                   // debug: put (addr >> 7) & 7 into the descriptor base-offset field
 };
 
 __device__ __forceinline__ float selu_fast(float x) {
@@ -41,11 +40,12 @@ __device__ __forceinline__ float selu_fast(float x) {
   return x > 0.f ? scale * x : (scale * alpha) * (ex2_approx(x * 1.4426950408889634f) - 1.0f);
 }
 
+// The A descriptor of a tap starts an arbitrary number of rows into the slab.  This relies on the swizzle being a
+// function of the shared-memory ADDRESS bits (chunk index ^= address bits [7,10)), which is what TMA wrote and what
+// the tensor core applies (verified on B200: the base-offset field must stay 0).
 template <int KW>
-__device__ __forceinline__ uint64_t a_desc(uint32_t addr, int bo_mode) {
-  uint64_t d = KW == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr);
-  if (bo_mode) d |= static_cast<uint64_t>((addr >> 7) & (KW == 64 ? 7u : 3u)) << 49;
-  return d;
+__device__ __forceinline__ uint64_t a_desc(uint32_t addr) {
+  return KW == 64 ? umma_desc_sw128(addr) : umma_desc_sw64(addr);
 }
 
 template <int KW, int CO, int NS>
@@ -109,6 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   if (warp == 0) {
@@ -158,22 +159,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
           for (int k = 0; k < KW / 16; ++k) {
             const uint64_t bh = KW == 64 ? umma_desc_sw128(wh + k * 32) : umma_desc_sw64(wh + k * 32);
-            mma_bf16_ss(d_tmem, a_desc<KW>(ah + k * 32, p.desc_bo), bh, idesc, first ^ 1u);
+            mma_bf16_ss(d_tmem, a_desc<KW>(ah + k * 32), bh, idesc, first ^ 1u);
             first = 0;
-            if (NS > 1) mma_bf16_ss(d_tmem, a_desc<KW>(al + k * 32, p.desc_bo), bh, idesc, 1u);
+            if (NS > 1) mma_bf16_ss(d_tmem, a_desc<KW>(al + k * 32), bh, idesc, 1u);
             if (NS == 3) {
               const uint64_t bl = KW == 64 ? umma_desc_sw128(wl + k * 32) : umma_desc_sw64(wl + k * 32);
-              mma_bf16_ss(d_tmem, a_desc<KW>(ah + k * 32, p.desc_bo), bl, idesc, 1u);
+              mma_bf16_ss(d_tmem, a_desc<KW>(ah + k * 32), bl, idesc, 1u);
             }
           }
         }
         mma_commit(empty_bar(s));
         mma_commit(tfull_bar(a));
       }
+      pdl_launch_dependents();
     }
   } else {
-    // ===== epilogue: TMEM lane quarter = warp % 4, one output row per thread =====
+    // ===== epilogue: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; one output row per thread =====
     const int q = warp & 3;
+    const int c_begin = ((warp - 2) >> 2) * (CO / 2), c_end = c_begin + CO / 2;
     const float* s_bias = s_par;
     const float* s_s1 = s_par + CO;
     const float* s_t1 = s_par + 2 * CO;
@@ -194,22 +197,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * CO;
 #pragma unroll 1
-      for (int c = 0; c < CO; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c, r);
-        float4 rs[8];
+      for (int c = c_begin; c < c_end; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + c, r);
+        float4 rs[4];
         if (p.resid && ok) {
           const float4* rp = reinterpret_cast<const float4*>(p.resid + m * CO + c);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rs[j] = rp[j];
+          for (int j = 0; j < 4; ++j) rs[j] = rp[j];
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 4; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           float x = __uint_as_float(r[i]) + s_bias[c + i];
           if (has1) x = fmaf(x, s_s1[c + i], s_t1[c + i]);
           if (p.act1 == ACT_SELU) x = selu_fast(x);
@@ -222,23 +225,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           if (p.out_f32) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + m * CO + c);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (p.out_hi) {
-            uint32_t hi[16], lo[16];
+            uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
               hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
               lo[j] = pack_bf16x2(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
             }
             uint4* oh = reinterpret_cast<uint4*>(p.out_hi + m * CO + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            oh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            oh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             if (p.out_lo) {
               uint4* ol = reinterpret_cast<uint4*>(p.out_lo + m * CO + c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
           }
         }
@@ -253,15 +256,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-}
-
-int desc_bo_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RTDF_CONV_DESC_BO");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
 }
 
 template <int KW, int CO, int NS>
@@ -301,7 +295,6 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
   p.bias = a.bias; p.s1 = a.s1; p.t1 = a.t1; p.act1 = a.act1; p.resid = a.resid;
   p.s2 = a.s2; p.t2 = a.t2; p.act2 = a.act2;
   p.out_f32 = a.out_f32; p.out_hi = a.out_hi; p.out_lo = a.out_lo;
-  p.desc_bo = desc_bo_mode();
 
   const TmapSwizzle sw = KW == 64 ? TMAP_SW128 : TMAP_SW64;
   CUtensorMap mAh, mAl, mWh, mWl;
@@ -323,7 +316,7 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
   }
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KW, CO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  conv_tc_kernel<KW, CO, NS><<<grid, kThreads, smem, stream>>>(mAh, mAl, mWh, mWl, p);
+  RTDF_CHECK_CUDA(launch_pdl(conv_tc_kernel<KW, CO, NS>, dim3(grid), dim3(kThreads), smem, stream, mAh, mAl, mWh, mWl, p));
   RTDF_LAUNCH_CHECK();
   return RTDF_OK;
 }

@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const TIn* __restrict__ in, long long rows, int C, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, int act, float* __restrict__ out_f32,
                bf16* __restrict__ out_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -290,7 +292,8 @@ static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const
   RTDF_REQUIRE(in && gamma && beta && rows > 0 && C > 0 && (out_f32 || out_bf16), "layernorm_rows: bad arguments");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if ((C & 127) == 0 && C <= 1024)
-    ln_rows_kernel<TIn><<<grid, 256, 0, s>>>(in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+    RTDF_CHECK_CUDA(launch_pdl(ln_rows_kernel<TIn>, dim3(grid), dim3(256), 0, s, in, rows, C, gamma, beta, eps, act, out_f32,
+                               out_bf16));
   else
     ln_rows_generic_kernel<TIn><<<grid, 256, 0, s>>>(in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
   RTDF_LAUNCH_CHECK();

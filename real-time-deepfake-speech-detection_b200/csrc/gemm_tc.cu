@@ -174,6 +174,62 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* box, int lane, const flo
                    pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
 }
 
+// Epilogue of one 128 x BN accumulator tile for one warp (32 rows, half of the columns): bias / activation / scale,
+// then TMA store (bf16 | fp32), TMA reduce-add (in-place fp32 residual) or direct global stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, const CUtensorMap* mapC, int mode, uint32_t t_row,
+                                                    const float* sb, int half, int lane, uint8_t* box_gen, uint32_t box,
+                                                    int n0, int row0, int batch, long long row, bool row_ok) {
+  constexpr int kColsPerWarp = BN / 2;
+  const int c_begin = half * kColsPerWarp, c_end = c_begin + kColsPerWarp;
+  if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 64) {
+      if (n0 + c >= p.N) break;  // warp-uniform
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_row + c, r0);
+      tmem_ld32(t_row + c + 32, r1);
+      tmem_ld_wait();
+      __align__(8) float o[64];
+      epilogue_math32(p.epi, r0, sb + c, o);
+      epilogue_math32(p.epi, r1, sb + c + 32, o + 32);
+      if (lane == 0) tma_store_wait_read<0>();   // previous store out of this box has drained
+      __syncwarp();
+      stage_row_bf16(box_gen, lane, o);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0 < p.rows_per_batch) {
+        tma_store_3d(mapC, box, n0 + c, row0, batch);
+        tma_store_commit();
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      if (n0 + c >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(t_row + c, r);
+      tmem_ld_wait();
+      __align__(8) float o[32];
+      epilogue_math32(p.epi, r, sb + c, o);
+      if (mode == EPI_TMA_F32 || mode == EPI_TMA_F32_ADD) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        stage_row_f32(box_gen, lane, o);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < p.rows_per_batch) {
+          if (mode == EPI_TMA_F32_ADD) tma_reduce_add_3d(mapC, box, n0 + c, row0, batch);
+          else tma_store_3d(mapC, box, n0 + c, row0, batch);
+          tma_store_commit();
+        }
+      } else {
+        epilogue_direct32(p.epi, o, row, n0 + c, p.N, row_ok);
+      }
+    }
+  }
+}
+
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (n-tile fastest so that concurrently
 // running CTAs share A rows in L2).  The smem ring runs across tile boundaries.
 template <int BN, int BK>
@@ -237,6 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                // the previous kernel's output (our A operand / residual) is complete and visible
   const uint32_t tmem_base = *tmem_ptr_gen;
   const int tiles_n = p.tiles_n, tiles_m = p.tiles_m;
 
@@ -295,6 +352,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mma_commit(tfull_bar(a));    // accumulator stage complete
       }
+      pdl_launch_dependents();       // all MMAs of this CTA are issued: the next kernel may start its prologue
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
@@ -325,55 +383,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (kLN ? 0 : a * BN);
       if (!kLN) {
-        constexpr int kColsPerWarp = BN / 2;
-        const float* sb = s_params + a * BN;
-        const int c_begin = half * kColsPerWarp, c_end = c_begin + kColsPerWarp;
-        if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
-#pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 64) {
-            if (n0 + c >= p.N) break;  // warp-uniform
-            uint32_t r0[32], r1[32];
-            tmem_ld32(t_row + c, r0);
-            tmem_ld32(t_row + c + 32, r1);
-            tmem_ld_wait();
-            __align__(8) float o[64];
-            epilogue_math32(p.epi, r0, sb + c, o);
-            epilogue_math32(p.epi, r1, sb + c + 32, o + 32);
-            if (lane == 0) tma_store_wait_read<0>();   // previous store out of this box has drained
-            __syncwarp();
-            stage_row_bf16(box_gen, lane, o);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && row0 < p.rows_per_batch) {
-              tma_store_3d(&mapC, box, n0 + c, row0, batch);
-              tma_store_commit();
-            }
-          }
-        } else {
-#pragma unroll 1
-          for (int c = c_begin; c < c_end; c += 32) {
-            if (n0 + c >= p.N) break;  // warp-uniform
-            uint32_t r[32];
-            tmem_ld32(t_row + c, r);
-            tmem_ld_wait();
-            __align__(8) float o[32];
-            epilogue_math32(p.epi, r, sb + c, o);
-            if (mode == EPI_TMA_F32 || mode == EPI_TMA_F32_ADD) {
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
-              stage_row_f32(box_gen, lane, o);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0 && row0 < p.rows_per_batch) {
-                if (mode == EPI_TMA_F32_ADD) tma_reduce_add_3d(&mapC, box, n0 + c, row0, batch);
-                else tma_store_3d(&mapC, box, n0 + c, row0, batch);
-                tma_store_commit();
-              }
-            } else {
-              epilogue_direct32(p.epi, o, row, n0 + c, p.N, row_ok);
-            }
-          }
-        }
+        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, s_params + a * BN, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
       } else {
         // y = act(LayerNorm_512(acc + bias)).  Two warps share a row (256 columns each): one TMEM pass for
         // (sum, sum of squares), partials exchanged through smem, one pass to normalise / activate / store.
@@ -457,6 +467,175 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+
+// =================================================================================================
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on one TPC owns a 256 x 256 output tile.  Each CTA loads its
+// own 128 A rows and ITS HALF of the W rows (32 KB per k-block instead of 48 KB for the same math per SM), the
+// leader CTA issues one M = 256 tcgen05.mma per k-step for both SMs, and each CTA runs the epilogue of its own 128
+// accumulator rows.  The 128 x 256 single-CTA tile is bound by the L2 -> shared-memory feed (profiles/r01_notes.md);
+// the pair tile needs 1.5x fewer bytes per flop.
+//   full[s]   (leader's copy)  : leader producer arrive.expect_tx(2 x stage) ; both CTAs' TMA loads complete_tx on it
+//   empty[s]  (each CTA's copy): multicast tcgen05.commit from the leader's MMA thread
+//   tfull[a]  (each CTA's copy): multicast tcgen05.commit ; tempty[a] (leader's copy): one arrive per epilogue warp of
+//                                both CTAs (remote mbarrier.arrive for the peer)
+// =================================================================================================
+template <int BK>
+struct Tc2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = 128 * BK * 2;               // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kParamBytes = 2 * BN * 4;
+  static constexpr int kFixed = kStagingBytes + 256 + kParamBytes;
+  static constexpr int kStagesRaw = (kMaxSmem - 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed + 1024;
+};
+
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BK>::kThreads, 1)
+tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapC, const TcKernelParams p) {
+  using Cfg = Tc2Cfg<BK>;
+  constexpr int BN = Cfg::BN;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiThreads = Cfg::kEpiWarps * 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int kOffStaging = kStages * Cfg::kStageBytes;
+  constexpr int kOffBars = kOffStaging + Cfg::kStagingBytes;
+  constexpr int kOffParams = kOffBars + 256;
+  const uint32_t bar_base = smem_base + kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBars + 8 * (2 * kStages + 4));
+  float* s_params = reinterpret_cast<float*>(smem_gen + kOffParams);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    if (p.epi_mode != EPI_DIRECT) prefetch_tmap(&mapC);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * Cfg::kEpiWarps);     // one elected arrive per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int tiles_n = p.tiles_n, tiles_m = p.tiles_m;       // tiles_m counts 256-row pair tiles
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      uint32_t it = 0;
+      for (int t = pair; t < p.total_tiles; t += n_pairs) {
+        const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+        const int m0 = m_tile * 256 + (int)rank * 128, nb0 = n_tile * BN + (int)rank * 128;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+          const uint32_t full_leader = mapa_shared(full_bar(s), 0);
+          const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
+          tma_load_3d_2sm(a_dst, &mapA, full_leader, kb * BK, m0, batch);
+          tma_load_2d_2sm(a_dst + Cfg::kABytes, &mapB, full_leader, kb * BK, nb0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = pair; t < p.total_tiles; t += n_pairs, ++lt) {
+        const int a = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(tempty_bar(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * Cfg::kStageBytes;
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_bf16_ss_2sm(d_tmem, make_desc(a_addr + k * 32, BK), make_desc(b_addr + k * 32, BK), idesc, (kb | k) != 0);
+          mma_commit_2sm(empty_bar(s), 3);   // both CTAs' smem slots
+        }
+        mma_commit_2sm(tfull_bar(a), 3);     // both CTAs' accumulator halves
+      }
+      pdl_launch_dependents();
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): this CTA's 128 accumulator rows =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    uint8_t* box_gen = smem_gen + kOffStaging + (warp - 2) * 4096;
+    const uint32_t box = smem_base + kOffStaging + (warp - 2) * 4096;
+    const int mode = p.epi_mode;
+    uint32_t lt = 0;
+    for (int t = pair; t < p.total_tiles; t += n_pairs, ++lt) {
+      const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+      const int m0 = m_tile * 256 + (int)rank * 128, n0 = n_tile * BN;
+      const int a = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      const int row0 = m0 + q * 32;
+      const int row_local = row0 + lane;
+      const bool row_ok = row_local < p.rows_per_batch;
+      const long long row = static_cast<long long>(batch) * p.rows_per_batch + row_local;
+      float* sb = s_params + a * BN;
+      for (int i = et; i < BN; i += kEpiThreads) sb[i] = (p.epi.bias && n0 + i < p.N) ? p.epi.bias[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      mbar_wait(tfull_bar(a), aph);
+      __syncwarp();
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+      epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();            // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 static int g_gelu_override = 0;
 void tc_set_gelu_variant(int act) { g_gelu_override = (act == ACT_GELU_TANH || act == ACT_GELU_AS) ? act : 0; }
 
@@ -467,6 +646,38 @@ static bool force_direct_epilogue() {
     v = (e && e[0] == 'd') ? 1 : 0;   // RTDF_TC_EPILOGUE=direct disables the TMA-store epilogue (debug / A-B runs)
   }
   return v == 1;
+}
+
+// Output path: a single output tensor goes through TMA stores (bf16 / fp32) or the TMA reduce-add (in-place residual).
+static int choose_epilogue_mode(TcKernelParams& p, CUtensorMap* mapC, const CUtensorMap* unused_map, const TcOperandA& A, int N,
+                                const TcEpilogue& epi, bool ln_variant, int BN) {
+  p.epi_mode = EPI_DIRECT;
+  const bool one_f32 = epi.out_f32 && !epi.out_bf16 && (epi.ld_f32 % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(epi.out_f32) % 16 == 0);
+  const bool one_bf16 = epi.out_bf16 && !epi.out_f32 && !epi.resid && (epi.ld_bf16 % 8 == 0) &&
+                        (reinterpret_cast<uintptr_t>(epi.out_bf16) % 16 == 0);
+  if (ln_variant) {
+    RTDF_REQUIRE(one_bf16, "tc_gemm: the LayerNorm variant writes exactly one bf16 output (16-byte aligned rows)");
+    p.epi_mode = EPI_TMA_BF16;
+  } else if (!force_direct_epilogue()) {
+    if (one_f32 && !epi.resid) p.epi_mode = EPI_TMA_F32;
+    else if (one_f32 && epi.resid == epi.out_f32 && epi.ldr == epi.ld_f32) p.epi_mode = EPI_TMA_F32_ADD;
+    else if (one_bf16 && BN >= 128) p.epi_mode = EPI_TMA_BF16;
+  }
+  if (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)epi.ld_f32 * 4, (uint64_t)epi.ld_f32 * 4 * (uint64_t)A.rows_per_batch};
+    uint32_t box[3] = {32, 32, 1};
+    RTDF_TRY(make_tmap_f32(mapC, epi.out_f32, 3, dims, strides, box, TMAP_SW128));
+  } else if (p.epi_mode == EPI_TMA_BF16) {
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)epi.ld_bf16 * 2, (uint64_t)epi.ld_bf16 * 2 * (uint64_t)A.rows_per_batch};
+    uint32_t box[3] = {64, 32, 1};
+    RTDF_TRY(make_tmap_bf16(mapC, epi.out_bf16, 3, dims, strides, box, TMAP_SW128));
+  } else {
+    *mapC = *unused_map;
+  }
+  return RTDF_OK;
 }
 
 template <int BN, int BK>
@@ -504,33 +715,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   }
   p.epi = epi;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
-  // ---- choose the output path: a single output tensor goes through TMA stores ----
-  p.epi_mode = EPI_DIRECT;
-  const bool one_f32 = epi.out_f32 && !epi.out_bf16 && (epi.ld_f32 % 4 == 0) &&
-                       (reinterpret_cast<uintptr_t>(epi.out_f32) % 16 == 0);
-  const bool one_bf16 = epi.out_bf16 && !epi.out_f32 && !epi.resid && (epi.ld_bf16 % 8 == 0) &&
-                        (reinterpret_cast<uintptr_t>(epi.out_bf16) % 16 == 0);
-  if (Cfg::kLN) {
-    RTDF_REQUIRE(one_bf16, "tc_gemm: the LayerNorm variant writes exactly one bf16 output (16-byte aligned rows)");
-    p.epi_mode = EPI_TMA_BF16;
-  } else if (!force_direct_epilogue()) {
-    if (one_f32 && !epi.resid) p.epi_mode = EPI_TMA_F32;
-    else if (one_f32 && epi.resid == epi.out_f32 && epi.ldr == epi.ld_f32) p.epi_mode = EPI_TMA_F32_ADD;
-    else if (one_bf16 && BN >= 128) p.epi_mode = EPI_TMA_BF16;
-  }
-  if (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD) {
-    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
-    uint64_t strides[2] = {(uint64_t)epi.ld_f32 * 4, (uint64_t)epi.ld_f32 * 4 * (uint64_t)A.rows_per_batch};
-    uint32_t box[3] = {32, 32, 1};
-    RTDF_TRY(make_tmap_f32(&mapC, epi.out_f32, 3, dims, strides, box, TMAP_SW128));
-  } else if (p.epi_mode == EPI_TMA_BF16) {
-    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
-    uint64_t strides[2] = {(uint64_t)epi.ld_bf16 * 2, (uint64_t)epi.ld_bf16 * 2 * (uint64_t)A.rows_per_batch};
-    uint32_t box[3] = {64, 32, 1};
-    RTDF_TRY(make_tmap_bf16(&mapC, epi.out_bf16, 3, dims, strides, box, TMAP_SW128));
-  } else {
-    mapC = mapA;  // unused
-  }
+  RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
@@ -542,7 +727,60 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     rec.variant = BN + (BK == 32 ? 1 : 0);
     RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
-  tc_gemm_kernel<BN, BK><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mapA, mapB, mapC, p);
+  RTDF_CHECK_CUDA(launch_pdl(tc_gemm_kernel<BN, BK>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, mapA, mapB,
+                             mapC, p));
+  RTDF_LAUNCH_CHECK();
+  if (g_prof_on) {
+    RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    g_prof.push_back(rec);
+  }
+  return RTDF_OK;
+}
+
+
+template <int BK>
+static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, const TcEpilogue& epi) {
+  using Cfg = Tc2Cfg<BK>;
+  static_assert(Cfg::kStages >= 3, "need at least three stages");
+  static_assert(8 * (2 * Cfg::kStages + 5) <= 256, "barrier block too small");
+  CUtensorMap mapA, mapB, mapC;
+  {
+    uint64_t dims[3] = {(uint64_t)A.k_extent, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)A.row_stride * 2, (uint64_t)(A.batches > 1 ? A.batch_stride : A.row_stride * A.rows_per_batch) * 2};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
+    RTDF_TRY(make_tmap_bf16(&mapA, A.ptr, 3, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)Kw * 2};
+    uint32_t box[2] = {(uint32_t)BK, 128};
+    RTDF_TRY(make_tmap_bf16(&mapB, W, 2, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
+  }
+  TcKernelParams p;
+  p.rows_per_batch = (int)A.rows_per_batch;
+  p.N = N;
+  p.num_kb = ceil_div(Kw, BK);
+  p.tiles_n = ceil_div(N, 256);
+  p.tiles_m = ceil_div((int)A.rows_per_batch, 256);
+  const long long total = (long long)p.tiles_n * p.tiles_m * A.batches;
+  RTDF_REQUIRE(total < (1LL << 31), "tc_gemm: too many tiles");
+  p.total_tiles = (int)total;
+  p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
+  p.epi = epi;
+  if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
+  RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, false, 256));
+  RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_2sm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
+  ProfRec rec{};
+  if (g_prof_on) {
+    RTDF_CHECK_CUDA(cudaEventCreate(&rec.a));
+    RTDF_CHECK_CUDA(cudaEventCreate(&rec.b));
+    rec.flops = 2.0 * (double)A.rows_per_batch * (double)A.batches * (double)N * (double)Kw;
+    rec.variant = 256;
+    RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
+  }
+  RTDF_CHECK_CUDA(launch_pdl(tc_gemm_2sm_kernel<BK>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, mapA, mapB,
+                             mapC, p));
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
@@ -565,6 +803,9 @@ int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int 
     case 64: return launch_variant<64, 64>(stream, A, W, N, Kw, mode, epi);
     case 128: return launch_variant<128, 64>(stream, A, W, N, Kw, mode, epi);
     case 256: return launch_variant<256, 64>(stream, A, W, N, Kw, mode, epi);
+    case 2256:   // CTA-pair (cta_group::2) 256 x 256 tiles
+      RTDF_REQUIRE(mode == TC_PLAIN, "tc_gemm: the CTA-pair variant implements plain GEMMs only");
+      return launch_2sm<64>(stream, A, W, N, Kw, epi);
     case 512:
     case 513:
       RTDF_REQUIRE(N == 512 && epi.ln_gamma && epi.ln_beta, "tc_gemm: LN variant needs N == 512 and LN parameters");

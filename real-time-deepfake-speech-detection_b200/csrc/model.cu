@@ -1,6 +1,8 @@
 // Context lifecycle, weight packing and the scoring forward (waveform -> XLS-R -> back-end -> logits).
 #include "model.cuh"
 
+#include <stdlib.h>
+
 #include "attention.cuh"
 #include "conformer.cuh"
 #include "conv_tc.cuh"
@@ -559,10 +561,20 @@ static SimtOperandA plainAf(const void* p, long long rows, long long k) {
   return a;
 }
 
+static bool gemm_2sm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_GEMM_2SM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // y = epilogue(A W^T): dispatch on the context precision
 static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long rows, const Lin& L, const TcEpilogue& e) {
   if (c->d.precision == RTDF_PREC_BF16) {
-    const int variant = L.n >= 256 ? 256 : (L.n >= 128 ? 128 : 64);
+    int variant = L.n >= 256 ? 256 : (L.n >= 128 ? 128 : 64);
+    if (variant == 256 && L.n % 256 == 0 && rows >= 2048 && gemm_2sm_enabled()) variant = 2256;   // CTA-pair tiles
     return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, variant, e);
   }
   return simt_gemm_f32(s, plainAf(A, rows, L.k), L.w, L.n, L.k, e);

@@ -2,6 +2,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace rtdf {
 
@@ -14,6 +15,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;   // measured on B200 (r01): the attribute costs ~2.5 % end to end, so it is opt-in
+  }
+  return v == 1;
+}
 
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }

@@ -129,7 +129,7 @@ def check_gemm_bf16(variants=(64, 128, 256)):
     g = torch.Generator().manual_seed(3)
     out = {}
     shapes = ((128, 256, 64), (300, 256, 128), (1000, 3072, 1024), (200, 144, 144), (131, 576, 144), (77, 1024, 4096),
-              (402, 128, 1024))
+              (402, 128, 1024), (5000, 1024, 256))     # the last one: more tiles than SMs (persistent loop, both stages)
     for M, N, K in shapes:
         A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
         W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)

@@ -32,7 +32,7 @@ def test_gemm_f32():
     kc.check_gemm_f32()
 
 
-@pytest.mark.parametrize("variant", [64, 128, 256])
+@pytest.mark.parametrize("variant", [64, 128, 256, 2256])
 def test_gemm_bf16_tcgen05(variant):
     kc.check_gemm_bf16(variants=(variant,))
 

@@ -46,7 +46,7 @@ def main():
         W = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(bf)
         bias = torch.randn(N, device=DEV)
         out = torch.empty(M, N, dtype=bf, device=DEV)
-        for v in (256, 128):
+        for v in (2256, 256, 128):
             ms = timeit(lambda: call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, 1.0, None, None, P(out), v, stream()))
             print(f"gemm {name:9s} N={N:4d} K={K:4d} variant {v}: {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s")
         if act == 1:

@@ -285,11 +285,17 @@ def run_b200(args):
         pms, pfl, pn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         native.check(lib.rtdf_profile_end(256, ctypes.byref(pms), ctypes.byref(pfl), ctypes.byref(pn)), "rtdf_profile_end")
         peaks = measured_peaks()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
         if pn.value > 0 and pms.value > 0:
             achieved = pfl.value / (pms.value * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<256,64> (QKV/out/FFN projections)",
+            roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM, 256-wide tiles: tc_gemm_2sm_kernel (CTA pair) / tc_gemm_kernel<256,64> (QKV/out/FFN projections)",
                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                        "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
+                            "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)",
                         "launches_timed": pn.value, "avg_launch_ms": pms.value / pn.value,
                         "flops_per_launch_avg": pfl.value / pn.value, "peak_source": peaks["source"] + ", sustained",
                         "whole_path_frac": value * GFLOP_PER_UTT * 1e9 / world / 1e12 / peaks["bf16_sustained"]}

@@ -612,7 +612,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       e.ln_beta = f.ln.b;
       e.out_bf16 = static_cast<bf16*>(nxt);
       e.ld_bf16 = 512;
-      RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, 512, e));
+      RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, 515, e));   // pipelined two-pass LN tile
     } else {
       SimtOperandA a;
       a.ptr = static_cast<const float*>(cur);

@@ -41,7 +41,7 @@ def test_gelu_epilogue_accuracy():
     kc.check_gelu_epilogue()
 
 
-@pytest.mark.parametrize("variant", [512, 513])
+@pytest.mark.parametrize("variant", [512, 513, 514, 515])
 def test_conv1d_implicit_gemm_ln_gelu(variant):
     kc.check_conv1d_tc(variants=(variant,))
 

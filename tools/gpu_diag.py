@@ -24,6 +24,8 @@ CHECKS = [
     ("gelu_epilogue", "tests.kernel_checks", "check_gelu_epilogue", {}),
     ("conv1d_tc_v512", "tests.kernel_checks", "check_conv1d_tc", {"variants": (512,)}),
     ("conv1d_tc_v513", "tests.kernel_checks", "check_conv1d_tc", {"variants": (513,)}),
+    ("conv1d_tc_v514", "tests.kernel_checks", "check_conv1d_tc", {"variants": (514,)}),
+    ("conv1d_tc_v515", "tests.kernel_checks", "check_conv1d_tc", {"variants": (515,)}),
     ("conv_planes_tc_x3", "tests.kernel_checks", "check_conv_planes_tc", {"nsplit": 3}),
     ("conv_planes_tc_x1", "tests.kernel_checks", "check_conv_planes_tc", {"nsplit": 1}),
     ("posconv", "tests.kernel_checks", "check_posconv", {}),

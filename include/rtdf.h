@@ -103,6 +103,13 @@ int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols
  * per 128 x variant tile) or 2256 (CTA pair, cta_group::2, per 256 x 256 tile). */
 int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const float* bias, int act, float scale,
                    const float* resid, float* out_f32, void* out_bf16, int variant, void* stream);
+/* Residual GEMM with the following LayerNorm fused behind it (the per-layer pattern out_proj -> LN, fc2 -> LN of
+ * fairseq's TransformerSentenceEncoderLayer):  x (M,N) fp32 += A W^T + bias, then, per 128-row block as soon as its
+ * last N-tile has been added,  ln_out = LN(x row) * gamma + beta  (bf16 and/or fp32).  counters: ceil(M/128) int32,
+ * zero on entry (left zero on exit).  variant 256 | 2256; N % 128 == 0, N <= 1024. */
+int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,
+                         const float* gamma, const float* beta, float eps, void* ln_out_bf16, float* ln_out_f32,
+                         int32_t* counters, int variant, void* stream);
 int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const float* bias, int act, float scale,
                   const float* resid, float* out_f32, void* stream);
 /* Strided 1-D conv as implicit GEMM on channels-last bf16 activations, fused bias + LayerNorm(512) + GELU:

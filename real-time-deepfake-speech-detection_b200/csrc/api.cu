@@ -64,6 +64,26 @@ int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const floa
                  make_epi(bias, act, scale, resid, out_f32, out_bf16, N));
 }
 
+int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,
+                         const float* gamma, const float* beta, float eps, void* ln_out_bf16, float* ln_out_f32,
+                         int32_t* counters, int variant, void* stream) {
+  RTDF_REQUIRE(x_inout && counters && gamma && beta, "rtdf_gemm_bf16_rowln: null argument");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(A);
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  TcEpilogue e = make_epi(bias, ACT_NONE, 1.0f, x_inout, x_inout, nullptr, N);
+  e.rowln_gamma = gamma;
+  e.rowln_beta = beta;
+  e.rowln_eps = eps;
+  e.rowln_out_bf16 = static_cast<bf16*>(ln_out_bf16);
+  e.rowln_out_f32 = ln_out_f32;
+  e.rowln_counters = counters;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant, e);
+}
+
 int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const float* bias, int act, float scale,
                   const float* resid, float* out_f32, void* stream) {
   RTDF_REQUIRE(out_f32, "rtdf_gemm_f32: no output");

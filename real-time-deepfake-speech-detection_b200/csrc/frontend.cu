@@ -1,6 +1,8 @@
 // Bandwidth-bound front-end kernels: coalesced, vectorised, warp-shuffle reductions.
 #include "frontend.cuh"
 
+#include <stdlib.h>
+
 namespace rtdf {
 
 // ------------------------------------------------------------------------------------------------
@@ -286,10 +288,87 @@ ln_rows_generic_kernel(const TIn* __restrict__ in, long long rows, int C, const 
   }
 }
 
+// Specialised LayerNorm(1024), fp32 in, no activation (the 49 LayerNorms of the transformer stack): everything is
+// compile-time, R rows per warp are in flight together, 4 warps per CTA.
+template <int R, bool kBf16Out>
+__global__ void __launch_bounds__(128)
+ln1024_kernel(const float* __restrict__ in, long long rows, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float eps, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
+  float4 v[R][8];
+#pragma unroll
+  for (int u = 0; u < R; ++u)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[u][j] = row0 + u < rows ? __ldcs(reinterpret_cast<const float4*>(in + (row0 + u) * 1024 + j * 128 + lane * 4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  float mean[R], rstd[R];
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+    mean[u] = warp_sum(s) * (1.0f / 1024.0f);
+  }
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = v[u][j].x - mean[u], b = v[u][j].y - mean[u], c = v[u][j].z - mean[u], d = v[u][j].w - mean[u];
+      q += a * a + b * b + c * c + d * d;
+    }
+    rstd[u] = rsqrtf(warp_sum(q) * (1.0f / 1024.0f) + eps);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c0 = j * 128 + lane * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      if (row0 + u >= rows) continue;
+      const float a = (v[u][j].x - mean[u]) * rstd[u] * g.x + bt.x;
+      const float b = (v[u][j].y - mean[u]) * rstd[u] * g.y + bt.y;
+      const float c = (v[u][j].z - mean[u]) * rstd[u] * g.z + bt.z;
+      const float d = (v[u][j].w - mean[u]) * rstd[u] * g.w + bt.w;
+      if (kBf16Out) *reinterpret_cast<uint2*>(out_bf16 + (row0 + u) * 1024 + c0) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+      else *reinterpret_cast<float4*>(out_f32 + (row0 + u) * 1024 + c0) = make_float4(a, b, c, d);
+    }
+  }
+}
+
+static int ln_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_LN_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 template <typename TIn>
 static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const float* gamma, const float* beta,
                      float eps, int act, float* out_f32, bf16* out_bf16) {
   RTDF_REQUIRE(in && gamma && beta && rows > 0 && C > 0 && (out_f32 || out_bf16), "layernorm_rows: bad arguments");
+  if (sizeof(TIn) == 4 && C == 1024 && act == ACT_NONE && (out_f32 != nullptr) != (out_bf16 != nullptr) && ln_variant() > 0) {
+    const float* inf = reinterpret_cast<const float*>(in);
+    const int R = ln_variant() >= 2 ? 2 : 1;
+    const unsigned g = (unsigned)((rows + 4 * R - 1) / (4 * R));
+    if (R == 2) {
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+    } else {
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+    }
+    RTDF_LAUNCH_CHECK();
+    return RTDF_OK;
+  }
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if ((C & 127) == 0 && C <= 1024)
     RTDF_CHECK_CUDA(launch_pdl(ln_rows_kernel<TIn>, dim3(grid), dim3(256), 0, s, in, rows, C, gamma, beta, eps, act, out_f32,

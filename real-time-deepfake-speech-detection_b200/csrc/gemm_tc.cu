@@ -230,6 +230,75 @@ __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, con
   }
 }
 
+// ---- fused row LayerNorm behind a residual GEMM (TcEpilogue::rowln_*) --------------------------------------------
+// Called by all epilogue warps of a CTA after the epilogue of one tile.  rb = 128-row block of that tile.
+template <int kEpiThreads>
+__device__ __forceinline__ void rowln_after_tile(const TcKernelParams& p, int rb, int row_begin, int et, int lane,
+                                                 volatile int* s_flag) {
+  const TcEpilogue& e = p.epi;
+  if (lane == 0) tma_store_wait_all<0>();      // this warp's TMA stores / reduce-adds of the tile have been performed
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+  if (et == 0) {
+    const int old = atomicAdd(e.rowln_counters + rb, 1);
+    const int last = old == p.tiles_n - 1;
+    if (last) e.rowln_counters[rb] = 0;       // ready for the next launch
+    __threadfence();
+    *s_flag = last;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+  if (!*s_flag) return;
+  // this CTA added the last N-tile of rows [row_begin, row_begin + 128): normalise them (warp per row, 2 rows in flight)
+  const int N = p.N, groups = N >> 7;
+  const float inv_n = 1.0f / (float)N;
+  const int w = et >> 5;
+  constexpr int kWarps = kEpiThreads / 32;
+  for (int r = w; r < 128; r += 2 * kWarps) {
+    float4 v[2][8];
+    long long rows[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      rows[u] = (long long)row_begin + r + u * kWarps;
+      const bool ok = r + u * kWarps < 128 && rows[u] < p.rows_per_batch;
+      if (!ok) rows[u] = -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < groups && ok) v[u][j] = __ldcg(reinterpret_cast<const float4*>(e.out_f32 + rows[u] * N + j * 128 + lane * 4));
+        else v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (rows[u] < 0) continue;       // warp-uniform
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[u][j].x + v[u][j].y + v[u][j].z + v[u][j].w;
+      const float mean = warp_sum(s) * inv_n;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < groups) {
+          const float a = v[u][j].x - mean, b = v[u][j].y - mean, c = v[u][j].z - mean, d = v[u][j].w - mean;
+          q += a * a + b * b + c * c + d * d;
+        }
+      const float rstd = rsqrtf(warp_sum(q) * inv_n + e.rowln_eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < groups) {
+          const int c0 = j * 128 + lane * 4;
+          const float4 g = *reinterpret_cast<const float4*>(e.rowln_gamma + c0);
+          const float4 bt = *reinterpret_cast<const float4*>(e.rowln_beta + c0);
+          const float a = (v[u][j].x - mean) * rstd * g.x + bt.x;
+          const float b = (v[u][j].y - mean) * rstd * g.y + bt.y;
+          const float c = (v[u][j].z - mean) * rstd * g.z + bt.z;
+          const float d = (v[u][j].w - mean) * rstd * g.w + bt.w;
+          if (e.rowln_out_f32) *reinterpret_cast<float4*>(e.rowln_out_f32 + rows[u] * N + c0) = make_float4(a, b, c, d);
+          if (e.rowln_out_bf16)
+            *reinterpret_cast<uint2*>(e.rowln_out_bf16 + rows[u] * N + c0) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+        }
+    }
+  }
+}
+
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  (n-tile fastest so that concurrently
 // running CTAs share A rows in L2).  The smem ring runs across tile boundaries.
 template <int BN, int BK>
@@ -456,6 +525,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand the stage back to the MMA warp
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
+      if (!kLN && p.epi.rowln_counters)
+        rowln_after_tile<kEpiThreads>(p, m_tile, m0, et, lane, reinterpret_cast<volatile int*>(smem_gen + kOffBars + 240));
     }
     if (lane == 0) tma_store_wait_all<0>();   // outstanding TMA stores complete before the CTA retires
   }
@@ -624,6 +695,8 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
+      if (p.epi.rowln_counters)
+        rowln_after_tile<kEpiThreads>(p, m_tile * 2 + (int)rank, m0, et, lane, reinterpret_cast<volatile int*>(smem_gen + kOffBars + 240));
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -917,6 +990,13 @@ static int choose_epilogue_mode(TcKernelParams& p, CUtensorMap* mapC, const CUte
     RTDF_TRY(make_tmap_bf16(mapC, epi.out_bf16, 3, dims, strides, box, TMAP_SW128));
   } else {
     *mapC = *unused_map;
+  }
+  if (epi.rowln_counters) {
+    RTDF_REQUIRE(!ln_variant && BN == 256 && (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD),
+                 "tc_gemm: the fused row LayerNorm needs a 256-wide variant with a single fp32 output");
+    RTDF_REQUIRE(A.batches == 1 && N % 128 == 0 && N <= 1024 && epi.ld_f32 == N && epi.rowln_gamma && epi.rowln_beta &&
+                 (epi.rowln_out_bf16 || epi.rowln_out_f32),
+                 "tc_gemm: fused row LayerNorm: N must be a multiple of 128 (<= 1024), dense rows, one batch");
   }
   return RTDF_OK;
 }

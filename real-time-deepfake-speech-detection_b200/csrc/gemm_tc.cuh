@@ -18,6 +18,17 @@ struct TcEpilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
+  // Row LayerNorm of the UPDATED fp32 output, fused behind the GEMM (256-wide variants, out_f32 written through TMA
+  // store / reduce-add, N <= 1024, N % 128 == 0, one batch): every CTA counts its finished tiles per 128-row block in
+  // rowln_counters (zero on entry, left zero on exit); the CTA that adds the last N-tile of a block normalises those rows:
+  //   rowln_out = LN(out_f32[row, :]) * rowln_gamma + rowln_beta          (bf16 and / or fp32, leading dimension N)
+  // Replaces the separate LayerNorm launch between out_proj / fc2 and the next projection.
+  const float* rowln_gamma = nullptr;
+  const float* rowln_beta = nullptr;
+  float rowln_eps = 1e-5f;
+  bf16* rowln_out_bf16 = nullptr;
+  float* rowln_out_f32 = nullptr;
+  int* rowln_counters = nullptr;
 };
 
 // A operand as a (k, row, batch) strided view of bf16 memory.  Plain GEMM: batches = 1.

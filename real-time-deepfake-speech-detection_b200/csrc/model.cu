@@ -461,6 +461,7 @@ struct FrontWs {
   void* attn;              // (M,1024)
   void* hbuf;              // (M,4096)
   float* feats;            // (M,1024) fp32
+  int* ln_cnt;             // per 128-row block tile counters of the fused GEMM + LayerNorm (zeroed each forward)
 };
 
 static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_feats, Bump& b, FrontWs* w) {
@@ -476,6 +477,7 @@ static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_
   w->attn = b.take<char>((long long)d.M * 1024 * es);
   w->hbuf = b.take<char>((long long)d.M * 4096 * es);
   w->feats = own_feats ? b.take<float>((long long)d.M * 1024) : nullptr;
+  w->ln_cnt = b.take<int>(d.M / 128 + 2);
 }
 
 struct AasistWs {
@@ -566,6 +568,15 @@ static bool gemm_2sm_enabled() {
   if (v < 0) {
     const char* e = getenv("RTDF_GEMM_2SM");
     v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static bool fuse_ln_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_FUSE_LN");
+    v = (e && e[0] == '1') ? 1 : 0;   // opt-in: at B=64 the in-GEMM LayerNorm jobs cost more than the 47 launches they replace
   }
   return v == 1;
 }
@@ -673,11 +684,16 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     RTDF_CHECK_CUDA(cudaMemcpyAsync(w.xb, w.x, (size_t)M * 1024 * 4, cudaMemcpyDeviceToDevice, s));
     RTDF_TRY(posconv_f32(s, w.x, static_cast<const float*>(w.xb), B, T, c->pos.w, c->pos.b));
   }
-  // transformer layers (pre-LN)
-  for (size_t l = 0; l < c->layers.size(); ++l) {
+  // transformer layers (pre-LN).  bf16 mode: every LayerNorm that follows a residual GEMM (LN2 after out_proj, the next
+  // layer's LN1 / the final encoder LN after fc2) runs inside that GEMM as soon as a 128-row block is complete.
+  const bool fuse_ln = bf && fuse_ln_enabled();
+  if (fuse_ln) RTDF_CHECK_CUDA(cudaMemsetAsync(w.ln_cnt, 0, (size_t)(M / 128 + 2) * sizeof(int), s));
+  const size_t n_layers = c->layers.size();
+  for (size_t l = 0; l < n_layers; ++l) {
     const XlsrLayer& L = c->layers[l];
-    RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln1.g, L.ln1.b, 1e-5f, ACT_NONE,
-                                bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
+    if (l == 0 || !fuse_ln)
+      RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln1.g, L.ln1.b, 1e-5f, ACT_NONE,
+                                  bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
     {
       TcEpilogue e;
       e.bias = L.qkv.b;
@@ -702,10 +718,14 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       e.ldr = 1024;
       e.out_f32 = w.x;
       e.ld_f32 = 1024;
+      if (fuse_ln) {
+        e.rowln_gamma = L.ln2.g; e.rowln_beta = L.ln2.b; e.rowln_out_bf16 = static_cast<bf16*>(w.xb); e.rowln_counters = w.ln_cnt;
+      }
       RTDF_TRY(linear(c, s, w.attn, M, L.out, e));
     }
-    RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln2.g, L.ln2.b, 1e-5f, ACT_NONE,
-                                bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
+    if (!fuse_ln)
+      RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln2.g, L.ln2.b, 1e-5f, ACT_NONE,
+                                  bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
     {
       TcEpilogue e;
       e.bias = L.fc1.b;
@@ -721,10 +741,20 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       e.ldr = 1024;
       e.out_f32 = w.x;
       e.ld_f32 = 1024;
+      if (fuse_ln) {
+        e.rowln_counters = w.ln_cnt;
+        if (l + 1 < n_layers) {
+          e.rowln_gamma = c->layers[l + 1].ln1.g; e.rowln_beta = c->layers[l + 1].ln1.b;
+          e.rowln_out_bf16 = static_cast<bf16*>(w.xb);
+        } else {
+          e.rowln_gamma = c->enc_ln.g; e.rowln_beta = c->enc_ln.b; e.rowln_out_f32 = feats;
+        }
+      }
       RTDF_TRY(linear(c, s, w.hbuf, M, L.fc2, e));
     }
   }
-  RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, c->enc_ln.g, c->enc_ln.b, 1e-5f, ACT_NONE, feats, nullptr));
+  if (!fuse_ln)
+    RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, c->enc_ln.g, c->enc_ln.b, 1e-5f, ACT_NONE, feats, nullptr));
   return RTDF_OK;
 }
 

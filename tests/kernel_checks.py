@@ -156,6 +156,38 @@ def check_gemm_bf16(variants=(64, 128, 256)):
     return out
 
 
+def check_gemm_rowln(variants=(256, 2256)):
+    """x += A W^T + b followed by the fused per-row-block LayerNorm (out_proj -> LN / fc2 -> LN pattern)."""
+    g = torch.Generator().manual_seed(13)
+    out = {}
+    for M, N, K in ((12736, 1024, 1024), (300, 1024, 256), (49, 1024, 4096), (1000, 512, 128), (5000, 1024, 64)):
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, generator=g)
+        x0 = torch.randn(M, N, generator=g) * 2
+        gamma = 1 + 0.1 * torch.randn(N, generator=g)
+        beta = 0.1 * torch.randn(N, generator=g)
+        xr = x0 + A.float() @ W.float().t() + b
+        ref = F.layer_norm(xr, (N,), gamma, beta, 1e-5)
+        Ad, Wd, bd, gd, btd = dev(A), dev(W), dev(b), dev(gamma), dev(beta)
+        for v in variants:
+            cnt = torch.zeros((M + 127) // 128, dtype=torch.int32, device=DEV)
+            for rep in range(3):          # repeated launches: counters must come back to zero, no race on the row blocks
+                x = x0.to(DEV)
+                o16 = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+                o32 = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+                call("rtdf_gemm_bf16_rowln", P(Ad), P(Wd), M, N, K, P(bd), P(x), P(gd), P(btd), 1e-5, P(o16), P(o32), P(cnt),
+                     v, stream())
+                dx = float((x.cpu() - xr).abs().max())
+                d32 = float((o32.cpu() - ref).abs().max())
+                d16 = float((o16.float().cpu() - ref).abs().max())
+                out[f"{M}x{N}x{K}_v{v}_rep{rep}"] = (dx, d32, d16)
+                assert int(cnt.abs().sum()) == 0, out
+                assert dx <= 2e-3 and d32 <= 2e-3, out        # fp32 accumulation order only
+                assert d16 <= 0.04, out                       # bf16 rounding of O(4) values
+    return out
+
+
 def check_gelu_epilogue():
     """The tensor-core epilogue GELUs against the exact erf GELU on a dense grid (identity GEMM, fp32 output).
     act 1 = sigmoid-of-quintic fit (product default), 4 = hardware-tanh form, 5 = A&S 7.1.26 erf."""

@@ -19,6 +19,7 @@ CHECKS = [
     ("gemm_f32", "tests.kernel_checks", "check_gemm_f32", {}),
     ("gemm_bf16_v256", "tests.kernel_checks", "check_gemm_bf16", {"variants": (256,)}),
     ("gemm_bf16_v2256_pair", "tests.kernel_checks", "check_gemm_bf16", {"variants": (2256,)}),
+    ("gemm_rowln", "tests.kernel_checks", "check_gemm_rowln", {}),
     ("gemm_bf16_v128", "tests.kernel_checks", "check_gemm_bf16", {"variants": (128,)}),
     ("gemm_bf16_v64", "tests.kernel_checks", "check_gemm_bf16", {"variants": (64,)}),
     ("gelu_epilogue", "tests.kernel_checks", "check_gelu_epilogue", {}),

@@ -62,6 +62,9 @@ typedef struct rtdf_taps {
   float* hidden;   /* (B, 160) AASIST read-out vector (xlsr_aasist.py:171-172)      */
   int32_t* idx_S;  /* (B, 21)  nodes kept by pool_S, descending score               */
   int32_t* idx_T;  /* (B, T'/2) nodes kept by pool_T                                */
+  float* layers;   /* (n_layers+1, B*T, 1024) residual stream entering layer 0 and leaving every transformer layer:
+                    * the I/O of `ssl_model.model.encoder.layers.N` that the KD forward hooks read
+                    * (trainer.py:176-195, main_kd.py:88-141)                      */
 } rtdf_taps;
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
@@ -145,6 +148,29 @@ int rtdf_conv_planes_tc(const void* in_hi, const void* in_lo, int ci, long long 
                         int hp_lo, int hp_hi, const float* bias, const float* s1, const float* t1, int act1,
                         const float* resid, const float* s2, const float* t2, int act2, float* out_f32,
                         void* out_hi, void* out_lo, int nsplit, void* stream);
+
+/* ---- the two ends of the path ------------------------------ */
+/* Fixed-length batch from ragged utterances (reference data/test_set.py:201-248 adjustDuration and
+ * adjustDuration_random_start), optionally fused with PreEmphasis (data/preprocess.py:22-27):
+ *   out[b][t] = fitted_b[t] - (preemph ? coef * fitted_b[t-1] : 0),  fitted_b[t] = src_b[(starts[b] + t) mod len_b],
+ *   fitted_b[-1] := fitted_b[1].  packed: concatenated fp32 samples (device), offsets: int64[batch+1] (device),
+ *   starts: int32[batch] or NULL (= 0; the reference draws it with random.randint on the host).  Utterances shorter
+ *   than `duration` are tile-repeated (they cross PCIe once), longer ones are cropped at starts[b]. */
+int rtdf_fit_duration(const float* packed, const long long* offsets, const int* starts, int batch, int duration,
+                      int preemph, float coef, float* out, void* stream);
+/* Score sink for one batch: scores[i] = logits[i][1] (main.py:212) and, when labels != NULL, the evaluation
+ * accumulators of Trainer._test (trainer.py:104-113) kept on the device: acc[0] += batch * CrossEntropyLoss(
+ * weight=class_weight, reduction='mean'), acc[1] += #(argmax == label), acc[2] += batch.  labels: int64[batch],
+ * class_weight: fp32[2] or NULL, scores: fp32[batch] or NULL, acc: double[3]. */
+int rtdf_score_sink(const float* logits, int batch, const long long* labels, const float* class_weight, float* scores,
+                    double* acc, void* stream);
+/* Integer ROC for the EER (trainer.py:134-139 calculate_EER): tp[i] / fp[i] = number of positives / negatives whose
+ * score is >= scores[i].  NaN scores (gather padding) are skipped and get tp = fp = -1.  labels: int64[n], 1 = bona fide. */
+int rtdf_roc_counts(const float* scores, const long long* labels, int n, int32_t* tp, int32_t* fp, void* stream);
+/* The two ROC points that bracket the EER: keys[0] = ((tp+fp) << 32 | tp) of the last point with
+ * 1 - fp/n_neg - tp/n_pos >= 0 (0 if only the origin qualifies), keys[1] = same packing for the first point past it. */
+int rtdf_roc_crossing(const int32_t* tp, const int32_t* fp, int n, long long n_pos, long long n_neg,
+                      unsigned long long* keys, void* stream);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* Total number of kernels this library has launched in the calling process. */

@@ -592,7 +592,7 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
 }
 
 static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dims& d, int preemph_on, float coef,
-                        const FrontWs& w, float* feats) {
+                        const FrontWs& w, float* feats, float* layer_taps = nullptr) {
   const bool bf = c->d.precision == RTDF_PREC_BF16;
   const int B = d.B, T = d.T;
   const long long M = d.M;
@@ -689,6 +689,8 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   const bool fuse_ln = bf && fuse_ln_enabled();
   if (fuse_ln) RTDF_CHECK_CUDA(cudaMemsetAsync(w.ln_cnt, 0, (size_t)(M / 128 + 2) * sizeof(int), s));
   const size_t n_layers = c->layers.size();
+  const size_t tap_bytes = (size_t)M * 1024 * sizeof(float);
+  if (layer_taps) RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
   for (size_t l = 0; l < n_layers; ++l) {
     const XlsrLayer& L = c->layers[l];
     if (l == 0 || !fuse_ln)
@@ -752,6 +754,8 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       }
       RTDF_TRY(linear(c, s, w.hbuf, M, L.fc2, e));
     }
+    if (layer_taps)   // output of encoder.layers[l] (the KD hook point, trainer.py:176-195)
+      RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps + (l + 1) * (size_t)M * 1024, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
   }
   if (!fuse_ln)
     RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, c->enc_ln.g, c->enc_ln.b, 1e-5f, ACT_NONE, feats, nullptr));
@@ -1201,7 +1205,7 @@ int rtdf_forward(rtdf_ctx* c, const float* wav, int B, int N, int preemph_on, fl
   RTDF_REQUIRE(b.off <= ws_bytes, "rtdf_forward: workspace too small (%zu < %zu bytes)", ws_bytes, b.off);
   RTDF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "rtdf_forward: workspace must be 256-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  RTDF_TRY(run_frontend(c, s, wav, d, preemph_on, coef, fw, fw.feats));
+  RTDF_TRY(run_frontend(c, s, wav, d, preemph_on, coef, fw, fw.feats, taps ? taps->layers : nullptr));
   if (taps && taps->feats)
     RTDF_CHECK_CUDA(cudaMemcpyAsync(taps->feats, fw.feats, (size_t)d.M * 1024 * 4, cudaMemcpyDeviceToDevice, s));
   return run_backend(c, s, fw.feats, B, d.T, logits, taps, aw, cw);

@@ -10,6 +10,7 @@ import copy
 import torch
 import torch.nn as nn
 
+from ._hooks import forward_with_hooks
 from ._rt import engine_for
 from .fe import *  # noqa: F401,F403
 from .fe import My_XLSR_FE, XLSR_FE
@@ -119,7 +120,7 @@ class _ConformerBase(nn.Module):
 
     def _score(self, x):
         x = x.squeeze(-1) if x.dim() == 3 else x
-        return self.engine().forward(x)
+        return forward_with_hooks(self, self.engine(), x)
 
 
 class Model(_ConformerBase):

@@ -8,6 +8,7 @@ back-end, read-out -- through librtdf.so; there is no PyTorch/CPU implementation
 import torch
 import torch.nn as nn
 
+from ._hooks import forward_with_hooks
 from ._rt import engine_for
 from .aasist_modules import *  # noqa: F401,F403
 from .fe import *  # noqa: F401,F403
@@ -71,7 +72,9 @@ class _AasistBase(nn.Module):
     def forward(self, x, return_taps=False):
         """x: (B,N) or (B,N,1) fp32 CUDA waveforms -> (B,2) logits  (reference forward, :86-177)."""
         x = x.squeeze(-1) if x.dim() == 3 else x
-        return self.engine().forward(x, want_taps=return_taps)
+        if return_taps:
+            return self.engine().forward(x, want_taps=True)
+        return forward_with_hooks(self, self.engine(), x)
 
 
 class XLSR_AASIST(_AasistBase):

@@ -49,6 +49,7 @@ class Engine:
             conf_kernel=int(conformer.get("kernel_size", 31)), conf_blocks=int(conformer.get("n_encoders", 4)),
             attention_impl=attention_impl, aasist_conv_impl=aasist_conv_impl)
         self.backend_kind = backend
+        self.n_layers = int(n_layers)
         self._ctx = ctypes.c_void_p()
         self._ws = None
         # CUDA graphs: the forward allocates nothing and never synchronises, so one captured graph per input
@@ -135,8 +136,12 @@ class Engine:
             raise ValueError(f"rtdf: expected (B,N) waveforms, got shape {tuple(wav.shape)}")
         return wav.to(torch.float32).contiguous()
 
-    def forward(self, wav, preemph=False, coef=0.97, want_taps=False):
-        """(B,N) fp32 CUDA waveforms -> (B,2) fp32 logits [, taps dict]."""
+    def forward(self, wav, preemph=False, coef=0.97, want_taps=False, layer_taps=False):
+        """(B,N) fp32 CUDA waveforms -> (B,2) fp32 logits [, taps dict].
+
+        layer_taps (with want_taps): also return taps['layers'], (n_layers+1, B, T, 1024) fp32 -- the residual
+        stream entering layer 0 and leaving each transformer layer (the I/O of ``encoder.layers.N`` that the
+        reference's KD forward hooks read, trainer.py:176-195)."""
         wav = self._check_wav(wav)
         B, N = wav.shape
         if B == 0:
@@ -152,6 +157,9 @@ class Engine:
                 T = self.num_frames(N)
                 taps["feats"] = torch.empty(B, T, 1024, dtype=torch.float32, device=self.device)
                 taps_struct = native.Taps(feats=taps["feats"].data_ptr())
+                if layer_taps:
+                    taps["layers"] = torch.empty(self.n_layers + 1, B, T, 1024, dtype=torch.float32, device=self.device)
+                    taps_struct.layers = taps["layers"].data_ptr()
                 if self.backend_kind == "aasist":
                     Tp = T // 3
                     taps["hidden"] = torch.empty(B, 160, dtype=torch.float32, device=self.device)

@@ -24,7 +24,8 @@ class ModelDesc(ctypes.Structure):
 
 
 class Taps(ctypes.Structure):
-    _fields_ = [("feats", c_void_p), ("hidden", c_void_p), ("idx_S", c_void_p), ("idx_T", c_void_p)]
+    _fields_ = [("feats", c_void_p), ("hidden", c_void_p), ("idx_S", c_void_p), ("idx_T", c_void_p),
+                ("layers", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/rtdf.h
@@ -60,6 +61,10 @@ SIGNATURES = {
     "rtdf_debug_gelu_variant": (c_int, [c_int]),
     "rtdf_profile_begin": (c_int, []),
     "rtdf_profile_end": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
+    "rtdf_fit_duration": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "rtdf_score_sink": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rtdf_roc_counts": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "rtdf_roc_crossing": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p]),
     "rtdf_graph_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -54,6 +54,7 @@ typedef struct rtdf_model_desc {
   int attention_impl; /* 0 = tcgen05 warp-specialised kernel, 1 = SIMT (debug), 2 = tcgen05 tile kernel (A/B) */
   int aasist_conv_impl; /* bf16 mode, residual-block + attention-map convs: 0 = tcgen05 with (hi,lo) bf16 operand
                          * pairs, 3 MMAs per product (~fp32 accuracy); 1 = tcgen05 plain bf16; 2 = fp32 SIMT */
+  int gat_impl;       /* bf16 mode, graph-attention rows: 0 = tensor cores (mma.sync, (hi,lo) bf16 pairs), 1 = fp32 SIMT */
 } rtdf_model_desc;
 
 /* Optional intermediate outputs of a forward call (device pointers, may be NULL). */
@@ -131,6 +132,18 @@ int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const
  * tensor memory), 1 = SIMT, 2 = tcgen05 one-tile-per-CTA kernel. */
 int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int heads, int is_bf16, int impl,
                    void* stream);
+/* Weights of one graph-attention row pass (device pointers).  *_t matrices are transposed to [D][DO]; bn_s / bn_t are the
+ * eval BatchNorm1d folded to scale / shift (NULL for the master row); a22 / a12 NULL for a homogeneous GAT. */
+typedef struct rtdf_gat_weights {
+  const float *att_w, *att_b, *a11, *a22, *a12, *with_t, *with_b, *without_t, *without_b, *bn_s, *bn_t;
+  float inv_temp;
+} rtdf_gat_weights;
+/* GraphAttentionLayer / HtrgGraphAttentionLayer rows (aasist_modules.py:17-294) on x (B,n,D) -> out (B,n,DO):
+ * e_ij = a . tanh(W (x_i*x_j) + b) / temp, softmax_j, aggregation, proj_with_att + proj_without_att, BN, SELU.
+ * n1: number of type-1 nodes (quadrant vectors a11 / a22 / a12); n1 = n for a homogeneous GAT.  master_in (B,D) with
+ * wm != NULL additionally updates the master node -> master_out (B,DO).  impl 0 = tensor cores, 1 = fp32 SIMT. */
+int rtdf_gat_rows(int d, int dout, const float* x, int batch, int n, int n1, const rtdf_gat_weights* w, float* out,
+                  const float* master_in, const rtdf_gat_weights* wm, float* master_out, int impl, void* stream);
 /* GraphPool (aasist_modules.py:306-338) on h (B,n,D): out (B,k,D), idx (B,k) descending score. */
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream);

@@ -62,6 +62,12 @@ int aasist_gat_rows(cudaStream_t s, int D, int DO, const GraphView& x, int B, in
                     float* out, long long out_batch_stride, const float* master_in, long long master_stride,
                     const GatRowWeights* wM, float* master_out);
 
+// Same contract on the tensor cores (gat_mma.cu): one warp per node, pair products built in registers, (hi, lo) bf16
+// operand pairs with three mma.sync per product (~fp32 accuracy).  Used by the bf16-mode back-end.
+int aasist_gat_rows_mma(cudaStream_t s, int D, int DO, const GraphView& x, int B, int n1, const GatRowWeights& w,
+                        float* out, long long out_batch_stride, const float* master_in, long long master_stride,
+                        const GatRowWeights* wM, float* master_out);
+
 // HS-GAL type projections: out[:, :n1] = W1 x1 + b1, out[:, n1:] = W2 x2 + b2     aasist_modules.py:159-164
 int aasist_type_proj(cudaStream_t s, int D, const GraphView& x1, const GraphView& x2, int B, const float* w1t,
                      const float* b1, const float* w2t, const float* b2, float* out);

@@ -200,6 +200,30 @@ int rtdf_profile_end(int variant, double* ms_total, double* flops_total, int* la
   return tc_profile_end(variant, ms_total, flops_total, launches);
 }
 
+static GatRowWeights gat_w(const rtdf_gat_weights* w) {
+  GatRowWeights g;
+  g.att_w = w->att_w; g.att_b = w->att_b; g.a11 = w->a11; g.a22 = w->a22; g.a12 = w->a12;
+  g.with_t = w->with_t; g.with_b = w->with_b; g.without_t = w->without_t; g.without_b = w->without_b;
+  g.bn_s = w->bn_s; g.bn_t = w->bn_t; g.inv_temp = w->inv_temp;
+  return g;
+}
+
+int rtdf_gat_rows(int d, int dout, const float* x, int batch, int n, int n1, const rtdf_gat_weights* w, float* out,
+                  const float* master_in, const rtdf_gat_weights* wm, float* master_out, int impl, void* stream) {
+  RTDF_REQUIRE(x && w && out, "rtdf_gat_rows: null argument");
+  GraphView v;
+  v.ptr = x;
+  v.n = n;
+  v.batch_stride = (long long)n * d;
+  const GatRowWeights g = gat_w(w);
+  GatRowWeights gm;
+  if (wm) gm = gat_w(wm);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 0)
+    return aasist_gat_rows_mma(s, d, dout, v, batch, n1, g, out, (long long)n * dout, master_in, d, wm ? &gm : nullptr, master_out);
+  return aasist_gat_rows(s, d, dout, v, batch, n1, g, out, (long long)n * dout, master_in, d, wm ? &gm : nullptr, master_out);
+}
+
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream) {
   GraphView g;

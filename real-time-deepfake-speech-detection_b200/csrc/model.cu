@@ -877,6 +877,14 @@ static int run_aasist_encoder_tc(rtdf_ctx* c, cudaStream_t s, int B, int Tp, con
   return attn_pool_planes(s, X.f, w.wmap, B, 42, Tp, Hp, Wp, a.pos_S, w.eS, w.eT);
 }
 
+static int gat_rows(const rtdf_ctx* c, cudaStream_t s, int D, int DO, const GraphView& x, int B, int n1,
+                    const GatRowWeights& w, float* out, long long out_bs, const float* master_in, long long master_stride,
+                    const GatRowWeights* wM, float* master_out) {
+  if (aasist_tc(c) && c->d.gat_impl == 0)
+    return aasist_gat_rows_mma(s, D, DO, x, B, n1, w, out, out_bs, master_in, master_stride, wM, master_out);
+  return aasist_gat_rows(s, D, DO, x, B, n1, w, out, out_bs, master_in, master_stride, wM, master_out);
+}
+
 static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, int T, const AasistWs& w, float* logits,
                       const rtdf_taps* taps) {
   const AasistW& a = c->aasist;
@@ -902,8 +910,8 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
   } else {
     RTDF_TRY(run_aasist_encoder_simt(c, s, B, Tp, w));
   }
-  RTDF_TRY(aasist_gat_rows(s, 64, 64, view(w.eS, 42, 42 * 64), B, 42, a.gat_S, w.gS, 42 * 64, nullptr, 0, nullptr, nullptr));
-  RTDF_TRY(aasist_gat_rows(s, 64, 64, view(w.eT, Tp, (long long)Tp * 64), B, Tp, a.gat_T, w.gT, (long long)Tp * 64, nullptr, 0, nullptr, nullptr));
+  RTDF_TRY(gat_rows(c, s, 64, 64, view(w.eS, 42, 42 * 64), B, 42, a.gat_S, w.gS, 42 * 64, nullptr, 0, nullptr, nullptr));
+  RTDF_TRY(gat_rows(c, s, 64, 64, view(w.eT, Tp, (long long)Tp * 64), B, Tp, a.gat_T, w.gT, (long long)Tp * 64, nullptr, 0, nullptr, nullptr));
   RTDF_TRY(aasist_graph_pool(s, 64, view(w.gS, 42, 42 * 64), B, a.pool_S.w, a.pool_S.b, 21, w.oS, w.idxS));
   RTDF_TRY(aasist_graph_pool(s, 64, view(w.gT, Tp, (long long)Tp * 64), B, a.pool_T.w, a.pool_T.b, kT, w.oT, w.idxT));
   const HsGalW* l1[2] = {&a.st11, &a.st21};
@@ -916,13 +924,13 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
     const AasistWs::Br& r = w.br[i];
     RTDF_TRY(aasist_type_proj(s, 64, view(w.oT, kT, (long long)kT * 64), view(w.oS, 21, 21 * 64), B, l1[i]->t1_wt,
                               l1[i]->t1_b, l1[i]->t2_wt, l1[i]->t2_b, r.hx));
-    RTDF_TRY(aasist_gat_rows(s, 64, 32, view(r.hx, n, (long long)n * 64), B, kT, l1[i]->rows, r.hy, (long long)n * 32,
+    RTDF_TRY(gat_rows(c, s, 64, 32, view(r.hx, n, (long long)n * 64), B, kT, l1[i]->rows, r.hy, (long long)n * 32,
                              master[i], 0, &l1[i]->master, r.ma));
     RTDF_TRY(aasist_graph_pool(s, 32, view(r.hy + (long long)kT * 32, 21, (long long)n * 32), B, pS[i]->w, pS[i]->b, 10, r.pS, nullptr));
     RTDF_TRY(aasist_graph_pool(s, 32, view(r.hy, kT, (long long)n * 32), B, pT[i]->w, pT[i]->b, kT2, r.pT, nullptr));
     RTDF_TRY(aasist_type_proj(s, 32, view(r.pT, kT2, (long long)kT2 * 32), view(r.pS, 10, 10 * 32), B, l2[i]->t1_wt,
                               l2[i]->t1_b, l2[i]->t2_wt, l2[i]->t2_b, r.hx2));
-    RTDF_TRY(aasist_gat_rows(s, 32, 32, view(r.hx2, n2, (long long)n2 * 32), B, kT2, l2[i]->rows, r.hy2, (long long)n2 * 32,
+    RTDF_TRY(gat_rows(c, s, 32, 32, view(r.hx2, n2, (long long)n2 * 32), B, kT2, l2[i]->rows, r.hy2, (long long)n2 * 32,
                              r.ma, 32, &l2[i]->master, r.mb));
   }
   ReadoutArgs ro;

@@ -27,7 +27,7 @@ class Engine:
     """
 
     def __init__(self, state_dict, device, backend, n_layers, precision=None, conformer=None,
-                 attention_impl=None, aasist_conv_impl=None, use_graph=None):
+                 attention_impl=None, aasist_conv_impl=None, use_graph=None, gat_impl=None):
         self.lib = native.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -40,6 +40,8 @@ class Engine:
             attention_impl = int(os.environ.get("RTDF_ATTENTION_IMPL", "0"))
         if aasist_conv_impl is None:
             aasist_conv_impl = int(os.environ.get("RTDF_AASIST_CONV_IMPL", "0"))
+        if gat_impl is None:
+            gat_impl = int(os.environ.get("RTDF_GAT_IMPL", "0"))
         desc = native.ModelDesc(
             backend={"aasist": native.BACKEND_AASIST, "conformer": native.BACKEND_CONFORMER,
                      None: native.BACKEND_NONE, "none": native.BACKEND_NONE}[backend],
@@ -47,7 +49,8 @@ class Engine:
             precision=native.PREC_BF16 if self.precision == "bf16" else native.PREC_FP32,
             conf_emb=int(conformer.get("emb_size", 144)), conf_heads=int(conformer.get("heads", 4)),
             conf_kernel=int(conformer.get("kernel_size", 31)), conf_blocks=int(conformer.get("n_encoders", 4)),
-            attention_impl=attention_impl, aasist_conv_impl=aasist_conv_impl)
+            attention_impl=attention_impl, aasist_conv_impl=aasist_conv_impl,
+            gat_impl=gat_impl)
         self.backend_kind = backend
         self.n_layers = int(n_layers)
         self._ctx = ctypes.c_void_p()

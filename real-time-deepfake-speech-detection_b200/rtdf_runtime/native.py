@@ -20,7 +20,12 @@ ACT_NONE, ACT_GELU, ACT_SWISH, ACT_SELU = 0, 1, 2, 3
 class ModelDesc(ctypes.Structure):
     _fields_ = [("backend", c_int), ("n_layers", c_int), ("precision", c_int), ("conf_emb", c_int),
                 ("conf_heads", c_int), ("conf_kernel", c_int), ("conf_blocks", c_int), ("attention_impl", c_int),
-                ("aasist_conv_impl", c_int)]
+                ("aasist_conv_impl", c_int), ("gat_impl", c_int)]
+
+
+class GatWeights(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("att_w", "att_b", "a11", "a22", "a12", "with_t", "with_b", "without_t",
+                                        "without_b", "bn_s", "bn_t")] + [("inv_temp", c_float)]
 
 
 class Taps(ctypes.Structure):
@@ -65,6 +70,8 @@ SIGNATURES = {
     "rtdf_score_sink": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rtdf_roc_counts": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_roc_crossing": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p]),
+    "rtdf_gat_rows": (c_int, [c_int, c_int, c_void_p, c_int, c_int, c_int, ctypes.POINTER(GatWeights), c_void_p, c_void_p,
+                              ctypes.POINTER(GatWeights), c_void_p, c_int, c_void_p]),
     "rtdf_graph_pool": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

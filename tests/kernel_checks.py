@@ -398,3 +398,70 @@ def check_graph_pool():
     call("rtdf_graph_pool", P(dev(h)), 1, 8, 32, P(dev(w)), P(dev(torch.zeros(1))), 4, P(o), P(io), stream())
     assert io.cpu().tolist() == [[0, 1, 2, 3]], io
     return out
+
+
+def _gat_weights(nat, keep, att, att_b, a11, a22, a12, with_l, without_l, bn, temp):
+    """ctypes rtdf_gat_weights from oracle sub-modules; `keep` holds the device tensors alive."""
+    def d(t):
+        t = dev(t.detach().float())
+        keep.append(t)
+        return t.data_ptr()
+    w = nat.GatWeights()
+    w.att_w, w.att_b, w.a11 = d(att), d(att_b), d(a11.reshape(-1))
+    w.a22 = d(a22.reshape(-1)) if a22 is not None else None
+    w.a12 = d(a12.reshape(-1)) if a12 is not None else None
+    w.with_t, w.with_b = d(with_l.weight.t().contiguous()), d(with_l.bias)
+    w.without_t, w.without_b = d(without_l.weight.t().contiguous()), d(without_l.bias)
+    if bn is not None:
+        s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        w.bn_s, w.bn_t = d(s), d(bn.bias - bn.running_mean * s)
+    w.inv_temp = 1.0 / temp
+    return w
+
+
+def check_gat_rows(impl=0):
+    """GraphAttentionLayer and HtrgGraphAttentionLayer rows (after the type projections) against the oracle."""
+    import ctypes
+    from oracle.aasist_ref import GraphAttentionLayer, HtrgGraphAttentionLayer, perturb_norm_stats
+    from tests.util import native
+    nat = native()
+    out = {}
+    torch.manual_seed(3)
+    tol = 2e-5 if impl == 1 else 2e-4
+    for B, n, D, DO, temp in ((3, 42, 64, 64, 2.0), (2, 66, 64, 64, 2.0), (2, 16, 64, 64, 2.0), (2, 1, 64, 64, 2.0),
+                              (2, 17, 64, 64, 0.5)):
+        layer = GraphAttentionLayer(D, DO, temperature=temp).eval()
+        perturb_norm_stats(layer, seed=5)
+        x = torch.randn(B, n, D)
+        with torch.no_grad():
+            ref = layer(x)
+        keep = []
+        w = _gat_weights(nat, keep, layer.att_proj.weight, layer.att_proj.bias, layer.att_weight, None, None,
+                         layer.proj_with_att, layer.proj_without_att, layer.bn, temp)
+        o = torch.empty(B, n, DO, device=DEV)
+        call("rtdf_gat_rows", D, DO, P(dev(x)), B, n, n, ctypes.byref(w), P(o), None, None, None, impl, stream())
+        d = float((o.cpu() - ref).abs().max())
+        out[f"gat_B{B}_n{n}"] = d
+        assert d <= tol, out
+    for B, n1, n2, D, DO, temp in ((3, 33, 21, 64, 32, 100.0), (2, 16, 10, 32, 32, 100.0), (2, 5, 3, 64, 32, 1.0),
+                                   (2, 1, 1, 32, 32, 100.0)):
+        layer = HtrgGraphAttentionLayer(D, DO, temperature=temp).eval()
+        perturb_norm_stats(layer, seed=6)
+        x1, x2, master = torch.randn(B, n1, D), torch.randn(B, n2, D), torch.randn(B, 1, D)
+        with torch.no_grad():
+            r1, r2, rm = layer(x1, x2, master=master)
+            xcat = torch.cat([layer.proj_type1(x1), layer.proj_type2(x2)], dim=1)   # type_proj_kernel's output
+        keep = []
+        w = _gat_weights(nat, keep, layer.att_proj.weight, layer.att_proj.bias, layer.att_weight11, layer.att_weight22,
+                         layer.att_weight12, layer.proj_with_att, layer.proj_without_att, layer.bn, temp)
+        wm = _gat_weights(nat, keep, layer.att_projM.weight, layer.att_projM.bias, layer.att_weightM, None, None,
+                          layer.proj_with_attM, layer.proj_without_attM, None, temp)
+        n = n1 + n2
+        o = torch.empty(B, n, DO, device=DEV)
+        mo = torch.empty(B, DO, device=DEV)
+        call("rtdf_gat_rows", D, DO, P(dev(xcat)), B, n, n1, ctypes.byref(w), P(o), P(dev(master.reshape(B, D))),
+             ctypes.byref(wm), P(mo), impl, stream())
+        d = max(float((o.cpu() - torch.cat([r1, r2], 1)).abs().max()), float((mo.cpu() - rm.reshape(B, DO)).abs().max()))
+        out[f"hsgal_B{B}_n{n1}+{n2}_D{D}"] = d
+        assert d <= tol, out
+    return out

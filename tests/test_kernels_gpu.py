@@ -67,3 +67,8 @@ def test_attention(impl):
 
 def test_graph_pool_bit_exact_topk():
     kc.check_graph_pool()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_graph_attention_rows(impl):
+    kc.check_gat_rows(impl)

@@ -124,8 +124,10 @@ int rtdf_conv1d_ln_gelu_bf16(const void* x, int batch, int l_in, int k, int stri
                              int variant, void* stream);
 /* Grouped positional conv (k=128, groups=16, pad 64, last frame dropped) + GELU + residual:
  * x_f32 (B,T,1024) += gelu(conv(x_bf16) + bias).  w packed [1024][128*64] bf16 (k index = tap*64 + ci). */
+/* impl 0 = slab-resident kernel (receptive field of a 256-frame tile loaded once, taps = descriptor row offsets),
+ * 1 = tap-shifted GEMM (A tile re-fetched per tap; kept for A/B timing). */
 int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames, const void* w_packed,
-                      const float* bias, void* stream);
+                      const float* bias, int impl, void* stream);
 int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const float* w_packed, const float* bias,
                      void* stream);
 /* qkv (B*T, 3*H*64) [q|k|v] with q pre-scaled -> ctx (B*T, H*64).  impl 0 = tcgen05 warp-specialised (P in

@@ -121,8 +121,11 @@ int rtdf_conv1d_ln_gelu_bf16(const void* x, int batch, int l_in, int k, int stri
 }
 
 int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames, const void* w_packed,
-                      const float* bias, void* stream) {
+                      const float* bias, int impl, void* stream) {
   RTDF_REQUIRE(x_f32 && x_bf16 && w_packed && bias, "rtdf_posconv_bf16: bad arguments");
+  if (impl == 0)
+    return posconv_tc(static_cast<cudaStream_t>(stream), x_f32, static_cast<const bf16*>(x_bf16), batch, n_frames,
+                      static_cast<const bf16*>(w_packed), bias);
   TcOperandA a;
   a.ptr = static_cast<const bf16*>(x_bf16);
   a.k_extent = 1024;

@@ -60,4 +60,8 @@ void tc_set_gelu_variant(int act);
 void tc_profile_begin();
 int tc_profile_end(int variant, double* ms_total, double* flops_total, int* launches);
 
+// Slab-resident grouped positional conv (posconv_tc.cu): x_f32 (B*T,1024) += gelu(conv_k128_g16(x_bf16) + bias);
+// w packed [1024][128*64] bf16 (k index = tap*64 + ci).  Any T >= 1 (256-frame tiles).
+int posconv_tc(cudaStream_t s, float* x_f32, const bf16* x_bf16, int B, int T, const bf16* w_packed, const float* bias);
+
 }  // namespace rtdf

@@ -572,6 +572,15 @@ static bool gemm_2sm_enabled() {
   return v == 1;
 }
 
+static bool posconv_slab_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_POSCONV_IMPL");
+    v = (e && e[0] == '1') ? 0 : 1;   // 1 = the tap-shifted GEMM it replaced (A/B timing)
+  }
+  return v == 1;
+}
+
 static bool fuse_ln_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -664,7 +673,9 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     RTDF_TRY(linear(c, s, w.featln, M, c->proj, e));
   }
   // x += GELU(pos_conv(x))
-  if (bf) {
+  if (bf && posconv_slab_enabled()) {
+    RTDF_TRY(posconv_tc(s, w.x, static_cast<const bf16*>(w.xb), B, T, c->pos.wb, c->pos.b));
+  } else if (bf) {
     TcOperandA a;
     a.ptr = static_cast<const bf16*>(w.xb);
     a.k_extent = 1024;

@@ -55,7 +55,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rtdf_gemm_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "rtdf_conv1d_ln_gelu_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
-    "rtdf_posconv_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rtdf_posconv_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "rtdf_posconv_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "rtdf_conv_planes_tc": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

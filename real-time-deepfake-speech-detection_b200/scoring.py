@@ -8,7 +8,8 @@ Mirrors what the reference's scoring callers do per batch -- ``produce_evaluatio
     (SURVEY.md section 8e); every rank holds a full weight replica, there is no data-path collective;
   * scores stay on the device and are exchanged with ONE all-gather of fp32[S] per rank
     (NCCL over NVLink on GPUs; gloo in the CPU tests of the host logic), tail padded with NaN;
-  * H2D copies come from pinned, double-buffered host memory on a side stream.
+  * H2D copies come from pinned host memory on a side stream, overlapped with the previous forward; the scores
+    of every batch are copied back asynchronously (``ScoringPipeline``).
 
 PyTorch supplies device memory, streams and torch.distributed; the forward itself is librtdf.so.
 """
@@ -50,36 +51,70 @@ def gather_scores(local_scores, n_items, per_rank, group=None):
     return recv[:n_items]
 
 
-class PinnedFeeder:
-    """Double-buffered pinned host -> device staging of (B,N) fp32 batches on a side stream."""
+class ScoringPipeline:
+    """The scoring loop of ``produce_evaluation_file`` (reference main.py:199-221) as a three-stage pipeline:
 
-    def __init__(self, batch_size, n_samples, device):
+      copy stream     H2D of batch i+1 from pinned host memory        (main.py:209  batch_x.to(device))
+      compute stream  forward of batch i (one CUDA-graph replay)       (main.py:210  model(batch_x))
+      compute stream  scores of batch i -> device vector -> async D2H  (main.py:212  batch_x[:, 1].data.cpu())
+
+    The reference serialises the three per batch (pageable copy, forward, blocking ``.cpu()``); here the host never
+    waits for the device inside the loop except to recycle one of `depth` input slots, and the only full
+    synchronisation is in ``finish``.  Every batch still crosses PCIe in both directions.
+    """
+
+    def __init__(self, model, capacity, batch_size, n_samples, device, preemph=False, coef=0.97, depth=2):
         self.device = torch.device(device)
-        self.host = [torch.empty(batch_size, n_samples, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.dev = [torch.empty(batch_size, n_samples, dtype=torch.float32, device=self.device) for _ in range(2)]
+        if self.device.type != "cuda":
+            raise RuntimeError("ScoringPipeline runs on CUDA devices only (no CPU path)")
+        self.eng = model.engine()
+        self.preemph, self.coef = preemph, coef
+        self.batch_size, self.n_samples = int(batch_size), int(n_samples)
+        self.dev_in = [torch.empty(batch_size, n_samples, dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(self.device)
-        self.ready = [torch.cuda.Event() for _ in range(2)]
-        self.free = [torch.cuda.Event() for _ in range(2)]
-        self.slot = 0
+        self.scores_dev = torch.full((max(int(capacity), 1),), PAD, dtype=torch.float32, device=self.device)
+        self.scores_host = torch.full((max(int(capacity), 1),), PAD, dtype=torch.float32).pin_memory()
+        self.count = 0
+        self.step = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
-    def stage(self, fill_fn, rows):
-        """fill_fn(host_view) writes `rows` utterances into pinned memory; returns (slot, rows)."""
-        s = self.slot
-        self.slot ^= 1
-        self.free[s].synchronize()          # the forward that consumed this slot has finished
-        fill_fn(self.host[s][:rows])
+    def push(self, host_batch):
+        """host_batch: (b, n_samples) fp32 CPU tensor, b <= batch_size; pinned memory makes the copy asynchronous."""
+        b = host_batch.shape[0]
+        if b == 0:
+            return
+        if b > self.batch_size or host_batch.shape[1] != self.n_samples:
+            raise ValueError(f"batch shape {tuple(host_batch.shape)} does not fit ({self.batch_size}, {self.n_samples})")
+        if self.count + b > self.scores_dev.numel():
+            raise ValueError("ScoringPipeline capacity exceeded")
+        slot = self.step % len(self.dev_in)
+        self.step += 1
+        self.free[slot].synchronize()                    # the forward that read this slot has finished
+        x = self.dev_in[slot][:b]
         with torch.cuda.stream(self.copy_stream):
-            self.dev[s][:rows].copy_(self.host[s][:rows], non_blocking=True)
-            self.ready[s].record(self.copy_stream)
-        return s, rows
+            x.copy_(host_batch, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[slot])
+        logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef)
+        self.free[slot].record(cur)
+        dst = self.scores_dev[self.count:self.count + b]
+        dst.copy_(logits[:, 1])                                                          # stays on the device ...
+        self.scores_host[self.count:self.count + b].copy_(dst, non_blocking=True)       # ... and goes home asynchronously
+        self.count += b
+        self.h2d_bytes += host_batch.numel() * 4
+        self.d2h_bytes += b * 4
 
-    def take(self, staged):
-        s, rows = staged
-        torch.cuda.current_stream(self.device).wait_event(self.ready[s])
-        return self.dev[s][:rows]
+    def device_scores(self):
+        return self.scores_dev[:self.count]
 
-    def release(self, staged):
-        self.free[staged[0]].record(torch.cuda.current_stream(self.device))
+    def finish(self):
+        """Synchronise once; returns the scores pushed so far as a CPU tensor (a view of pinned memory)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.scores_host[:self.count]
 
 
 def score_utterances(model, n_items, load_batch, n_samples, batch_size, device, rank=0, world=1, group=None,
@@ -91,21 +126,16 @@ def score_utterances(model, n_items, load_batch, n_samples, batch_size, device, 
     eval mode on `device`.
     """
     lo, hi, per = shard_range(n_items, rank, world)
-    feeder = PinnedFeeder(batch_size, n_samples, device)
-    local = torch.empty(max(hi - lo, 0), dtype=torch.float32, device=device)
-    ranges = batch_ranges(lo, hi, batch_size)
-    eng = model.engine()
-    staged = feeder.stage(lambda out, r=ranges[0]: load_batch(r[0], r[1], out), ranges[0][1] - ranges[0][0]) if ranges else None
-    for i, (b_lo, b_hi) in enumerate(ranges):
-        cur = staged
-        if i + 1 < len(ranges):
-            nxt = ranges[i + 1]
-            staged = feeder.stage(lambda out, r=nxt: load_batch(r[0], r[1], out), nxt[1] - nxt[0])
-        x = feeder.take(cur)
-        logits = eng.forward(x, preemph=preemph, coef=coef)          # main.py:210
-        local[b_lo - lo: b_hi - lo] = logits[:, 1]                    # main.py:212 (kept on device)
-        feeder.release(cur)
-    return gather_scores(local, n_items, per, group)
+    pipe = ScoringPipeline(model, max(hi - lo, 1), batch_size, n_samples, device, preemph=preemph, coef=coef, depth=2)
+    host = [torch.empty(batch_size, n_samples, dtype=torch.float32).pin_memory() for _ in range(3)]
+    for i, (b_lo, b_hi) in enumerate(batch_ranges(lo, hi, batch_size)):
+        # 3 host buffers for 2 device slots: push(i) waits for forward(i-2), whose H2D (the last reader of buffer
+        # (i-2) % 3 ... and of buffer i % 3 = (i-3) % 3) is then complete
+        out = host[i % 3][: b_hi - b_lo]
+        load_batch(b_lo, b_hi, out)
+        pipe.push(out)
+    torch.cuda.current_stream(torch.device(device)).synchronize()
+    return gather_scores(pipe.device_scores(), n_items, per, group)
 
 
 def write_score_file(path, utt_ids, scores):

@@ -144,3 +144,27 @@ def test_layer_taps_and_forward_hooks(precision, tol):
         scale = want[k][1].abs().max()
         assert (xin.transpose(0, 1).cpu() - want[k][0]).abs().max() <= tol * scale
         assert (xout.transpose(0, 1).cpu() - want[k][1]).abs().max() <= tol * scale
+
+
+def test_scoring_pipeline_matches_direct_forward_bit_exactly():
+    """H2D / forward / D2H pipelining must not change a single score (ragged last batch included)."""
+    from oracle import models_ref as O
+    scoring = pkg("scoring")
+    _, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=1, order="first")
+    N, B = 16000, 4
+    x = O.synth_waveforms(11, N, seed=5)
+    with torch.no_grad():
+        want = torch.cat([prod(x[i:i + B].cuda())[:, 1].cpu() for i in range(0, 11, B)])
+    pipe = scoring.ScoringPipeline(prod, 11, B, N, "cuda")
+    for i in range(0, 11, B):
+        pipe.push(x[i:i + B].pin_memory())
+    got = pipe.finish()
+    assert torch.equal(got, want)
+    assert pipe.h2d_bytes == 11 * N * 4 and pipe.d2h_bytes == 11 * 4
+    with pytest.raises(ValueError):
+        pipe.push(x[:1].pin_memory())            # capacity exceeded
+
+    def load(lo, hi, out):
+        out.copy_(x[lo:hi])
+    all_scores = scoring.score_utterances(prod, 11, load, N, B, "cuda")
+    assert torch.equal(all_scores.cpu(), want)

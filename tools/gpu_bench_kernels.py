@@ -100,8 +100,9 @@ def main():
     xb = xf.to(bf)
     w = (torch.randn(1024, 8192, device=DEV) / 90).to(bf)
     bias = torch.randn(1024, device=DEV)
-    ms = timeit(lambda: call("rtdf_posconv_bf16", P(xf), P(xb), B, T, P(w), P(bias), stream()), iters=5)
-    print(f"posconv: {ms:7.3f} ms  {2.0 * M * 1024 * 64 * 128 / ms / 1e9:8.1f} TFLOP/s")
+    for impl in (0, 1):
+        ms = timeit(lambda: call("rtdf_posconv_bf16", P(xf), P(xb), B, T, P(w), P(bias), impl, stream()), iters=5)
+        print(f"posconv impl {impl}: {ms:7.3f} ms  {2.0 * M * 1024 * 64 * 128 / ms / 1e9:8.1f} TFLOP/s")
 
 
 if __name__ == "__main__":

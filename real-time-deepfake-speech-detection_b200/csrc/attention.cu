@@ -296,42 +296,68 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       tc_fence_after();
       float sum = 1.f;
       if (warp_active) {
-        float mx = -INFINITY;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c * 16, v);
-          tmem_ld_wait();
-          if (c * 16 + 16 <= T) {
+        // Two passes over the S row in 32-column chunks, software-pipelined: the tcgen05.ld of chunk c+1 is in
+        // flight while chunk c is reduced / exponentiated (the loads' ~latency was the top stall of the
+        // one-load-one-wait version: long_scoreboard 33 % of samples, MUFU pipe 29 % busy).
+        const int nch = (p.Tk + 31) >> 5;
+        uint32_t va[32], vb[32];
+        float mx = -INFINITY, mx1 = -INFINITY;
+        auto chunk_max = [&](const uint32_t (&v)[32], int c) {
+          if (c * 32 + 32 <= T) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4) {
+              mx = max3(mx, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              mx1 = max3(mx1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c * 16 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        };
+        tmem_ld32(t_row, va);
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait_regs(va);
+          if (c + 1 < nch) tmem_ld32(t_row + (c + 1) * 32, vb);
+          chunk_max(va, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait_regs(vb);
+            if (c + 2 < nch) tmem_ld32(t_row + (c + 2) * 32, va);
+            chunk_max(vb, c + 1);
           }
         }
-        const float mxs = mx * kLog2e;
+        tmem_ld32(t_row, va);             // first chunk of the second pass
+        const float mxs = fmaxf(mx, mx1) * kLog2e;
         sum = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c * 16, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
-          const bool fullc = c * 16 + 16 <= T;      // warp-uniform
+        auto chunk_exp = [&](const uint32_t (&v)[32], int c) {
+          uint32_t pk[16];
+          const bool fullc = c * 32 + 32 <= T;      // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 16; ++j) {
             float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mxs));
             float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mxs));
             if (!fullc) {
-              if (c * 16 + 2 * j >= T) e0 = 0.f;
-              if (c * 16 + 2 * j + 1 >= T) e1 = 0.f;
+              if (c * 32 + 2 * j >= T) e0 = 0.f;
+              if (c * 32 + 2 * j + 1 >= T) e1 = 0.f;
             }
             // accumulate the bf16-rounded probabilities so that numerator and denominator agree
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
             sum += __low2float(h2) + __high2float(h2);
             pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          tmem_st8(t_row + c * 8, pk);          // P chunk c overwrites S columns [8c, 8c+8), already consumed
+          // P chunk c overwrites S columns [16c, 16c+16): already consumed, and behind the chunk in flight
+          tmem_st8(t_row + c * 16, pk);
+          tmem_st8(t_row + c * 16 + 8, pk + 8);
+        };
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait_regs(va);
+          if (c + 1 < nch) tmem_ld32(t_row + (c + 1) * 32, vb);
+          chunk_exp(va, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait_regs(vb);
+            if (c + 2 < nch) tmem_ld32(t_row + (c + 2) * 32, va);
+            chunk_exp(vb, c + 1);
+          }
         }
         tmem_st_wait();
       }

@@ -1,5 +1,6 @@
 // Bandwidth-bound front-end kernels: coalesced, vectorised, warp-shuffle reductions.
 #include "frontend.cuh"
+#include "gemm_tc.cuh"
 
 #include <stdlib.h>
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c,
 
 constexpr int kConv0FramesPerCta = 256;   // 8 warps x 8 groups of 4 frames: the 26 KB parameter block is loaded once
 
-template <typename TOut>
+template <typename TOut, bool kTanhGelu = false>
 __global__ void __launch_bounds__(256, 2)
 conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -180,8 +181,8 @@ conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restri
           float2 y0 = fma2(acc[f][2 * j], mul2(make_float2(gv.x, gv.y), rstd2), make_float2(bv.x, bv.y));
           float2 y1 = fma2(acc[f][2 * j + 1], mul2(make_float2(gv.z, gv.w), rstd2), make_float2(bv.z, bv.w));
           if (sizeof(TOut) == 2) {   // bf16 output: the fitted GELU (|err| <= 2.6e-5) is far below the rounding step
-            y0 = gelu2(y0);
-            y1 = gelu2(y1);
+            y0 = kTanhGelu ? gelu2_tanh(y0) : gelu2(y0);
+            y1 = kTanhGelu ? gelu2_tanh(y1) : gelu2(y1);
           } else {
             y0 = make_float2(gelu_erf(y0.x), gelu_erf(y0.y));
             y1 = make_float2(gelu_erf(y1.x), gelu_erf(y1.y));
@@ -201,6 +202,8 @@ int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
   dim3 grid(ceil_div(L1, kConv0FramesPerCta), B);
   if (out_f32)
     conv0_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_f32);
+  else if (tc_get_gelu_variant() == ACT_GELU_TANH)
+    conv0_kernel<bf16, true><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16);
   else
     conv0_kernel<bf16><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16);
   RTDF_LAUNCH_CHECK();

@@ -951,6 +951,7 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 static int g_gelu_override = 0;
+int tc_get_gelu_variant() { return g_gelu_override; }
 void tc_set_gelu_variant(int act) { g_gelu_override = (act == ACT_GELU_TANH || act == ACT_GELU_AS) ? act : 0; }
 
 static bool force_direct_epilogue() {

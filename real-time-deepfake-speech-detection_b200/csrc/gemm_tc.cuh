@@ -55,6 +55,7 @@ int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int 
 
 // A/B switch for timing runs: evaluate ACT_GELU epilogues with ACT_GELU_TANH / ACT_GELU_AS (0 = default)
 void tc_set_gelu_variant(int act);
+int tc_get_gelu_variant();
 
 // per-launch CUDA-event timing of tc_gemm launches (variant: 64|128|256|512|513, or -1 = all)
 void tc_profile_begin();

@@ -104,7 +104,8 @@ int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w_tapmaj
 int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
                         const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream);
 /* D = act(A W^T + bias) * scale + resid.  A: (M,K) bf16, W: (N,K) bf16.  variant: tile width 64|128|256 (one CTA
- * per 128 x variant tile) or 2256 (CTA pair, cta_group::2, per 256 x 256 tile). */
+ * per 128 x variant tile), 2256 (CTA pair, cta_group::2, per 256 x 256 tile) or 1064 (64-wide tiles with split-K over
+ * the idle SMs when the call is an in-place residual update, out_f32 == resid: the streaming-chunk regime). */
 int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const float* bias, int act, float scale,
                    const float* resid, float* out_f32, void* out_bf16, int variant, void* stream);
 /* Residual GEMM with the following LayerNorm fused behind it (the per-layer pattern out_proj -> LN, fc2 -> LN of

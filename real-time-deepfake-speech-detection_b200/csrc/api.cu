@@ -60,8 +60,12 @@ int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const floa
   a.rows_per_batch = M;
   a.batches = 1;
   a.row_stride = K;
-  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant,
-                 make_epi(bias, act, scale, resid, out_f32, out_bf16, N));
+  TcEpilogue e = make_epi(bias, act, scale, resid, out_f32, out_bf16, N);
+  if (variant == 1064) {      // 64-wide tiles with automatic split-K (in-place residual form only)
+    e.k_splits = 0;
+    variant = 64;
+  }
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant, e);
 }
 
 int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,

@@ -33,6 +33,8 @@ struct TcKernelParams {
   int tiles_n, tiles_m, total_tiles;
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
   int epi_mode;
+  int k_splits = 1;        // split-K: tile t covers k-blocks [split * kb_per_split, ...) and reduce-adds its partial
+  int kb_per_split = 0;
   TcEpilogue epi;
 };
 
@@ -371,10 +373,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // ===== TMA producer =====
       uint32_t it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+        const int split = t % p.k_splits, tt = t / p.k_splits;
+        const int n_tile = tt % tiles_n, m_tile = (tt / tiles_n) % tiles_m, batch = tt / (tiles_n * tiles_m);
         const int m0 = m_tile * BM, n0 = n_tile * BN;
         const int a_col0 = n_tile * p.a_col_per_ntile;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
@@ -401,7 +405,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(tempty_bar(a), aph ^ 1);     // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (kLN ? 0 : a * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int kb0 = (t % p.k_splits) * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(full_bar(s), ph);
@@ -414,7 +419,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int h = 0; h < (BN + 255) / 256; ++h) {
               const uint64_t bdesc = make_desc(b_addr + h * 256 * BK * 2 + k * 32, BK);
-              mma_bf16_ss(d_tmem + h * 256, adesc, bdesc, idesc, (kb | k) != 0);
+              mma_bf16_ss(d_tmem + h * 256, adesc, bdesc, idesc, ((kb - kb0) | k) != 0);
             }
           }
           mma_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
@@ -433,7 +438,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int mode = p.epi_mode;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+      const int split = t % p.k_splits, tt = t / p.k_splits;
+      const int n_tile = tt % tiles_n, m_tile = (tt / tiles_n) % tiles_m, batch = tt / (tiles_n * tiles_m);
       const int m0 = m_tile * BM, n0 = n_tile * BN;
       const int a = lt % kAcc;
       const uint32_t aph = (lt / kAcc) & 1;
@@ -444,7 +450,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (!kLN) {
         // stage this tile's bias slice (double-buffered by accumulator stage)
         float* sb = s_params + a * BN;
-        for (int i = et; i < BN; i += kEpiThreads) sb[i] = (p.epi.bias && n0 + i < p.N) ? p.epi.bias[n0 + i] : 0.f;
+        for (int i = et; i < BN; i += kEpiThreads)      // the bias rides on the first K split only
+          sb[i] = (p.epi.bias && split == 0 && n0 + i < p.N) ? p.epi.bias[n0 + i] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       mbar_wait(tfull_bar(a), aph);
@@ -1038,6 +1045,20 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   p.epi = epi;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
+  if (epi.k_splits != 1 && mode == TC_PLAIN && !Cfg::kLN && p.epi_mode == EPI_TMA_F32_ADD && epi.act == ACT_NONE &&
+      !epi.rowln_counters) {
+    // Skinny residual GEMM (few output tiles, long K): split K over otherwise idle SMs; every split reduce-adds its
+    // partial into the fp32 output (TMA reduce at L2), so no second pass is needed.
+    int want = epi.k_splits > 1 ? epi.k_splits : kNumSMs / p.total_tiles;
+    if (want > p.num_kb / 2) want = p.num_kb / 2;
+    if (want > 1) {
+      p.kb_per_split = ceil_div(p.num_kb, want);
+      p.k_splits = ceil_div(p.num_kb, p.kb_per_split);
+      p.total_tiles *= p.k_splits;
+    }
+  }
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;

@@ -14,6 +14,9 @@ struct TcEpilogue {
   long long ld_f32 = 0;
   bf16* out_bf16 = nullptr;        // optional bf16 output
   long long ld_bf16 = 0;
+  // split-K for skinny in-place residual GEMMs (out_f32 == resid, no activation; single-CTA variants): 1 = off,
+  // 0 = as many splits as there are idle SMs, n > 1 = n splits.  Partials meet in the TMA reduce-add.
+  int k_splits = 1;
   // row-LayerNorm fused epilogue (only for the N == 512 full-row variant): y = act(LN(acc + bias))
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;

@@ -581,6 +581,16 @@ static bool posconv_slab_enabled() {
   return v == 1;
 }
 
+constexpr long long kSkinnyRows = 512;
+static bool skinny_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_SKINNY_GEMM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool fuse_ln_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -595,6 +605,14 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
   if (c->d.precision == RTDF_PREC_BF16) {
     int variant = L.n >= 256 ? 256 : (L.n >= 128 ? 128 : 64);
     if (variant == 256 && L.n % 256 == 0 && rows >= 2048 && gemm_2sm_enabled()) variant = 2256;   // CTA-pair tiles
+    if (rows <= kSkinnyRows && L.n % 64 == 0 && skinny_enabled()) {
+      // Streaming chunks (batch 1-8 x 49 frames, or one 4 s utterance): the GEMM is a weight-streaming problem, so
+      // the tile count -- not the tile shape -- sets the time.  64-wide tiles (4x the CTAs of the 256-wide ones)
+      // and split-K on the in-place residual GEMMs put (nearly) every SM on the weight stream.
+      TcEpilogue es = e;
+      es.k_splits = 0;
+      return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, es);
+    }
     return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, variant, e);
   }
   return simt_gemm_f32(s, plainAf(A, rows, L.k), L.w, L.n, L.k, e);

@@ -156,6 +156,27 @@ def check_gemm_bf16(variants=(64, 128, 256)):
     return out
 
 
+def check_gemm_splitk():
+    """Skinny in-place residual GEMMs (streaming chunks): 64-wide tiles with split-K, partials met by TMA reduce-add."""
+    g = torch.Generator().manual_seed(13)
+    out = {}
+    for M, N, K in ((49, 1024, 4096), (49, 1024, 1024), (199, 1024, 4096), (392, 1024, 1024), (8, 128, 1024), (49, 64, 128)):
+        A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, generator=g)
+        R = torch.randn(M, N, generator=g)
+        ref = (A.float() @ W.float().t() + b) * 0.5 + R
+        o = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=0, scale=0.5, resid=R.to(DEV), variant=1064, inplace=True)
+        d = float((o.cpu() - ref).abs().max())
+        out[f"{M}x{N}x{K}"] = d
+        assert d <= 2e-3, out
+        # with an activation the call must fall back to a single split and still be right
+        o2 = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=1.0, resid=R.to(DEV), variant=1064, inplace=True)
+        d2 = float((o2.cpu() - (F.gelu(A.float() @ W.float().t() + b) + R)).abs().max())
+        assert d2 <= 2e-3, (out, d2)
+    return out
+
+
 def check_gemm_rowln(variants=(256, 2256)):
     """x += A W^T + b followed by the fused per-row-block LayerNorm (out_proj -> LN / fc2 -> LN pattern)."""
     g = torch.Generator().manual_seed(13)

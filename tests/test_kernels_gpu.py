@@ -37,6 +37,10 @@ def test_gemm_bf16_tcgen05(variant):
     kc.check_gemm_bf16(variants=(variant,))
 
 
+def test_gemm_split_k_reduce_add():
+    kc.check_gemm_splitk()
+
+
 @pytest.mark.parametrize("variant", [256, 2256])
 def test_gemm_with_fused_row_layernorm(variant):
     kc.check_gemm_rowln(variants=(variant,))

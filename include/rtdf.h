@@ -104,17 +104,27 @@ int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w_tapmaj
 int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
                         const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream);
 /* D = act(A W^T + bias) * scale + resid.  A: (M,K) bf16, W: (N,K) bf16.  variant: tile width 64|128|256 (one CTA
- * per 128 x variant tile), 2256 (CTA pair, cta_group::2, per 256 x 256 tile) or 1064 (64-wide tiles with split-K over
- * the idle SMs when the call is an in-place residual update, out_f32 == resid: the streaming-chunk regime). */
+ * per 128 x variant tile) or 2256 (CTA pair, cta_group::2, per 256 x 256 tile). */
 int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const float* bias, int act, float scale,
                    const float* resid, float* out_f32, void* out_bf16, int variant, void* stream);
 /* Residual GEMM with the following LayerNorm fused behind it (the per-layer pattern out_proj -> LN, fc2 -> LN of
  * fairseq's TransformerSentenceEncoderLayer):  x (M,N) fp32 += A W^T + bias, then, per 128-row block as soon as its
  * last N-tile has been added,  ln_out = LN(x row) * gamma + beta  (bf16 and/or fp32).  counters: ceil(M/128) int32,
- * zero on entry (left zero on exit).  variant 256 | 2256; N % 128 == 0, N <= 1024. */
+ * zero on entry (left zero on exit).  variant 256 | 2256 | 64; N % 128 == 0, N <= 1024. */
 int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,
                          const float* gamma, const float* beta, float eps, void* ln_out_bf16, float* ln_out_f32,
                          int32_t* counters, int variant, void* stream);
+/* Skinny GEMMs of streaming chunks (batch 1-8 x 1 s: M = 49..392 rows): the op is a weight stream, so K is split over
+ * the otherwise idle SMs.  rtdf_gemm_plan_splits gives the number of splits S for a shape (1 = not split);
+ * rtdf_gemm_bf16_splitk (S > 1 only) writes split s's partial sum of A W^T (+ bias on split 0) to
+ * partials[s][M][N] fp32 (64-wide tiles, plain TMA stores);  rtdf_layernorm_accum_rows (N = 1024) folds them into the
+ * residual stream in split order -- x += sum_s partials[s], written back -- and emits LN(x) as bf16 or fp32.  Together
+ * they replace  x += out_proj(attn) ; LN  and  x += fc2(h) ; LN  of a transformer layer, bit-reproducibly. */
+int rtdf_gemm_plan_splits(int M, int N, int K);
+int rtdf_gemm_bf16_splitk(const void* A, const void* W, int M, int N, int K, const float* bias, float* partials,
+                          void* stream);
+int rtdf_layernorm_accum_rows(float* x, const float* partials, int n_splits, long long rows, const float* gamma,
+                              const float* beta, float eps, float* out_f32, void* out_bf16, void* stream);
 int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const float* bias, int act, float scale,
                   const float* resid, float* out_f32, void* stream);
 /* Strided 1-D conv as implicit GEMM on channels-last bf16 activations, fused bias + LayerNorm(512) + GELU:

@@ -60,12 +60,31 @@ int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const floa
   a.rows_per_batch = M;
   a.batches = 1;
   a.row_stride = K;
-  TcEpilogue e = make_epi(bias, act, scale, resid, out_f32, out_bf16, N);
-  if (variant == 1064) {      // 64-wide tiles with automatic split-K (in-place residual form only)
-    e.k_splits = 0;
-    variant = 64;
-  }
-  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant, e);
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant,
+                 make_epi(bias, act, scale, resid, out_f32, out_bf16, N));
+}
+
+int rtdf_gemm_plan_splits(int M, int N, int K) { return tc_plan_splits(M, N, K); }
+
+int rtdf_gemm_bf16_splitk(const void* A, const void* W, int M, int N, int K, const float* bias, float* partials,
+                          void* stream) {
+  RTDF_REQUIRE(A && W && partials, "rtdf_gemm_bf16_splitk: null argument");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(A);
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  TcEpilogue e;
+  e.bias = bias;
+  e.partials = partials;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, 64, e);
+}
+
+int rtdf_layernorm_accum_rows(float* x, const float* partials, int n_splits, long long rows, const float* gamma,
+                              const float* beta, float eps, float* out_f32, void* out_bf16, void* stream) {
+  return layernorm_accum_rows(static_cast<cudaStream_t>(stream), x, partials, n_splits, rows, gamma, beta, eps, out_f32,
+                              static_cast<bf16*>(out_bf16));
 }
 
 int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,

@@ -58,9 +58,10 @@ typedef __nv_bfloat16 bf16;
 // become resident and run their prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous
 // kernel drains; pdl_wait() then blocks until that kernel has completed and its writes are visible.  Every kernel
 // launched through launch_pdl() MUST call pdl_wait() before its first global-memory access that depends on (or
-// could overwrite the inputs of) the previous kernel.  Opt-in with RTDF_PDL=1 (it measured slower than plain stream
-// order inside the CUDA graph on B200, profiles/r01_notes.md).
+// could overwrite the inputs of) the previous kernel.  On for small problems (B*T <= 1024 rows: streaming chunks, ~5 %
+// lower latency), off for large ones (2.5 % slower inside the CUDA graph at batch 64); RTDF_PDL=0/1 forces it.
 bool pdl_enabled();
+void pdl_set_auto(bool on);   // set per forward call from the problem size (model.cu)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -345,6 +345,70 @@ ln1024_kernel(const float* __restrict__ in, long long rows, const float* __restr
   }
 }
 
+// Same normalisation behind a split-K GEMM: the row of the residual stream first takes the K-split partial sums
+// (x += sum_s partials[s], added in split order, so the result does not depend on which CTA finished first), is
+// written back, and is normalised from registers.
+template <bool kBf16Out>
+__global__ void __launch_bounds__(128)
+ln1024_accum_kernel(float* __restrict__ x, const float* __restrict__ partials, int n_splits, long long split_stride,
+                    long long rows, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                    float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  // one row per CTA (rows are few in this regime): thread t owns columns [8t, 8t+8)
+  __shared__ float red[2][4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  float* xr = x + row * 1024 + t * 8;
+  float4 v0 = *reinterpret_cast<const float4*>(xr), v1 = *reinterpret_cast<const float4*>(xr + 4);
+  const float* pr = partials + row * 1024 + t * 8;
+#pragma unroll 4
+  for (int sp = 0; sp < n_splits; ++sp) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(pr + sp * split_stride));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(pr + sp * split_stride + 4));
+    v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
+    v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+  }
+  *reinterpret_cast<float4*>(xr) = v0;
+  *reinterpret_cast<float4*>(xr + 4) = v1;
+  float s = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w));
+  if (lane == 0) red[0][wid] = s;
+  __syncthreads();
+  const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) * (1.0f / 1024.0f);
+  const float d0 = v0.x - mean, d1 = v0.y - mean, d2 = v0.z - mean, d3 = v0.w - mean;
+  const float d4 = v1.x - mean, d5 = v1.y - mean, d6 = v1.z - mean, d7 = v1.w - mean;
+  float q = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 + d4 * d4 + d5 * d5 + d6 * d6 + d7 * d7);
+  if (lane == 0) red[1][wid] = q;
+  __syncthreads();
+  const float rstd = rsqrtf(((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) * (1.0f / 1024.0f) + eps);
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + t * 8), g1 = *reinterpret_cast<const float4*>(gamma + t * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + t * 8), b1 = *reinterpret_cast<const float4*>(beta + t * 8 + 4);
+  const float y0 = d0 * rstd * g0.x + b0.x, y1 = d1 * rstd * g0.y + b0.y, y2 = d2 * rstd * g0.z + b0.z, y3 = d3 * rstd * g0.w + b0.w;
+  const float y4 = d4 * rstd * g1.x + b1.x, y5 = d5 * rstd * g1.y + b1.y, y6 = d6 * rstd * g1.z + b1.z, y7 = d7 * rstd * g1.w + b1.w;
+  if (kBf16Out) {
+    *reinterpret_cast<uint4*>(out_bf16 + row * 1024 + t * 8) =
+        make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
+  } else {
+    *reinterpret_cast<float4*>(out_f32 + row * 1024 + t * 8) = make_float4(y0, y1, y2, y3);
+    *reinterpret_cast<float4*>(out_f32 + row * 1024 + t * 8 + 4) = make_float4(y4, y5, y6, y7);
+  }
+}
+
+int layernorm_accum_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, const float* gamma,
+                         const float* beta, float eps, float* out_f32, bf16* out_bf16) {
+  RTDF_REQUIRE(x && partials && n_splits >= 1 && rows > 0 && gamma && beta && ((out_f32 != nullptr) != (out_bf16 != nullptr)),
+               "layernorm_accum_rows: bad arguments");
+  const unsigned g = (unsigned)rows;
+  if (out_bf16)
+    RTDF_CHECK_CUDA(launch_pdl(ln1024_accum_kernel<true>, dim3(g), dim3(128), 0, s, x, partials, n_splits, rows * 1024, rows,
+                               gamma, beta, eps, out_f32, out_bf16));
+  else
+    RTDF_CHECK_CUDA(launch_pdl(ln1024_accum_kernel<false>, dim3(g), dim3(128), 0, s, x, partials, n_splits, rows * 1024, rows,
+                               gamma, beta, eps, out_f32, out_bf16));
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
 static int ln_variant() {
   static int v = -1;
   if (v < 0) {

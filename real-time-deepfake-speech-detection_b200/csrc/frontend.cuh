@@ -21,6 +21,11 @@ int layernorm_rows_f32(cudaStream_t s, const float* in, long long rows, int C, c
 int layernorm_rows_bf16(cudaStream_t s, const bf16* in, long long rows, int C, const float* gamma, const float* beta,
                         float eps, int act, float* out_f32, bf16* out_bf16);
 
+// LayerNorm(1024) behind a split-K GEMM: x (rows,1024) fp32 += sum_s partials[s] (s = 0..n_splits-1, each (rows,1024),
+// added in that order), x is written back, then out = LN(x) as bf16 or fp32.
+int layernorm_accum_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, const float* gamma,
+                         const float* beta, float eps, float* out_f32, bf16* out_bf16);
+
 // fp32 verification path of the grouped positional conv: x (B,T,1024) fp32, w packed [1024][128*64]
 // (k index = tap*64 + ci), out x += gelu(conv + bias)
 int posconv_f32(cudaStream_t s, float* x, const float* xin, int B, int T, const float* w_packed, const float* bias);

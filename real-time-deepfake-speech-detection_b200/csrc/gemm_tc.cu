@@ -243,7 +243,7 @@ __device__ __forceinline__ void rowln_after_tile(const TcKernelParams& p, int rb
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
   if (et == 0) {
     const int old = atomicAdd(e.rowln_counters + rb, 1);
-    const int last = old == p.tiles_n - 1;
+    const int last = old == p.tiles_n * p.k_splits - 1;      // every N-tile (and K split) of the block has been added
     if (last) e.rowln_counters[rb] = 0;       // ready for the next launch
     __threadfence();
     *s_flag = last;
@@ -459,7 +459,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (kLN ? 0 : a * BN);
       if (!kLN) {
-        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, s_params + a * BN, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
+        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, s_params + a * BN, half, lane, box_gen, box, n0, row0,
+                                p.k_splits > 1 ? split : batch, row, row_ok);
       } else {
         // y = act(LayerNorm_512(acc + bias)).  Two warps share a row (256 columns each): one TMEM pass for
         // (sum, sum of squares), partials exchanged through smem, one pass to normalise / activate / store.
@@ -1000,8 +1001,8 @@ static int choose_epilogue_mode(TcKernelParams& p, CUtensorMap* mapC, const CUte
     *mapC = *unused_map;
   }
   if (epi.rowln_counters) {
-    RTDF_REQUIRE(!ln_variant && BN == 256 && (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD),
-                 "tc_gemm: the fused row LayerNorm needs a 256-wide variant with a single fp32 output");
+    RTDF_REQUIRE(!ln_variant && (BN == 256 || BN == 64) && (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD),
+                 "tc_gemm: the fused row LayerNorm needs a 256- or 64-wide variant with a single fp32 output");
     RTDF_REQUIRE(A.batches == 1 && N % 128 == 0 && N <= 1024 && epi.ld_f32 == N && epi.rowln_gamma && epi.rowln_beta &&
                  (epi.rowln_out_bf16 || epi.rowln_out_f32),
                  "tc_gemm: fused row LayerNorm: N must be a multiple of 128 (<= 1024), dense rows, one batch");
@@ -1047,17 +1048,25 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
   p.k_splits = 1;
   p.kb_per_split = p.num_kb;
-  if (epi.k_splits != 1 && mode == TC_PLAIN && !Cfg::kLN && p.epi_mode == EPI_TMA_F32_ADD && epi.act == ACT_NONE &&
-      !epi.rowln_counters) {
-    // Skinny residual GEMM (few output tiles, long K): split K over otherwise idle SMs; every split reduce-adds its
-    // partial into the fp32 output (TMA reduce at L2), so no second pass is needed.
-    int want = epi.k_splits > 1 ? epi.k_splits : kNumSMs / p.total_tiles;
-    if (want > p.num_kb / 2) want = p.num_kb / 2;
-    if (want > 1) {
-      p.kb_per_split = ceil_div(p.num_kb, want);
-      p.k_splits = ceil_div(p.num_kb, p.kb_per_split);
-      p.total_tiles *= p.k_splits;
-    }
+  if (epi.partials) {
+    // Deterministic split-K for skinny GEMMs: split s writes its partial sum (bias on split 0) to partials[s] with plain
+    // TMA stores; the consumer (layernorm_accum_rows) folds them into the residual stream in a fixed order.
+    RTDF_REQUIRE(mode == TC_PLAIN && !Cfg::kLN && BN == 64 && A.batches == 1 && epi.act == ACT_NONE && !epi.resid &&
+                 !epi.out_bf16 && !epi.rowln_counters && epi.scale == 1.0f,
+                 "tc_gemm: split-K partials need a plain 64-wide GEMM without activation / residual / bf16 output");
+    const int splits = tc_plan_splits(A.rows_per_batch, N, Kw);
+    RTDF_REQUIRE(splits > 1, "tc_gemm: split-K requested for a shape that tc_plan_splits() does not split");
+    p.kb_per_split = ceil_div(p.num_kb, splits);
+    p.k_splits = ceil_div(p.num_kb, p.kb_per_split);
+    RTDF_REQUIRE(p.k_splits == splits, "tc_gemm: inconsistent split plan");
+    p.total_tiles *= p.k_splits;
+    p.epi.out_f32 = epi.partials;
+    p.epi.ld_f32 = N;
+    p.epi_mode = EPI_TMA_F32;
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)p.k_splits};
+    uint64_t strides[2] = {(uint64_t)N * 4, (uint64_t)N * 4 * (uint64_t)A.rows_per_batch};
+    uint32_t box[3] = {32, 32, 1};
+    RTDF_TRY(make_tmap_f32(&mapC, epi.partials, 3, dims, strides, box, TMAP_SW128));
   }
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
@@ -1182,6 +1191,17 @@ static int launch_conv_ln(cudaStream_t stream, const TcOperandA& A, const bf16* 
     g_prof.push_back(rec);
   }
   return RTDF_OK;
+}
+
+int tc_plan_splits(long long rows, int N, int Kw) {
+  const long long tiles = ((rows + BM - 1) / BM) * ((N + 63) / 64);
+  const int num_kb = (Kw + 63) / 64;
+  long long want = tiles > 0 ? kNumSMs / tiles : 1;
+  if (want > num_kb / 2) want = num_kb / 2;
+  if (want > 8) want = 8;
+  if (want < 2) return 1;
+  const int per = (num_kb + (int)want - 1) / (int)want;
+  return (num_kb + per - 1) / per;
 }
 
 int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, int mode, int variant,

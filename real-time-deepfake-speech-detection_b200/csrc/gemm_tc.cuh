@@ -14,9 +14,10 @@ struct TcEpilogue {
   long long ld_f32 = 0;
   bf16* out_bf16 = nullptr;        // optional bf16 output
   long long ld_bf16 = 0;
-  // split-K for skinny in-place residual GEMMs (out_f32 == resid, no activation; single-CTA variants): 1 = off,
-  // 0 = as many splits as there are idle SMs, n > 1 = n splits.  Partials meet in the TMA reduce-add.
-  int k_splits = 1;
+  // Deterministic split-K for skinny GEMMs (64-wide variant, no activation / residual): when set, split s of
+  // tc_plan_splits(rows, N, K) writes its partial sum (bias on split 0) to partials[s][rows][N] (fp32) instead of any
+  // other output; the consumer adds them up in a fixed order (layernorm_accum_rows).
+  float* partials = nullptr;
   // row-LayerNorm fused epilogue (only for the N == 512 full-row variant): y = act(LN(acc + bias))
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
@@ -55,6 +56,10 @@ enum TcMode {
 //          513 -> same with BK 32 / 64-byte swizzle (deeper pipeline)
 int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int Kw, int mode, int variant,
             const TcEpilogue& epi);
+
+// Number of K splits tc_gemm uses for a (rows, N, K) problem in partials mode: enough to put the idle SMs on the
+// weight stream, at most 8, at least two 64-wide k-blocks per split; 1 = do not split.
+int tc_plan_splits(long long rows, int N, int Kw);
 
 // A/B switch for timing runs: evaluate ACT_GELU epilogues with ACT_GELU_TANH / ACT_GELU_AS (0 = default)
 void tc_set_gelu_variant(int act);

@@ -450,6 +450,9 @@ static int make_dims(int B, int N, Dims* d) {
   return RTDF_OK;
 }
 
+constexpr long long kSkinnyRows = 512;   // B*T up to which GEMMs are treated as weight-streaming problems
+constexpr long long kPdlRows = 1024;     // B*T up to which programmatic dependent launch is switched on
+
 struct FrontWs {
   float* wav_pe;           // pre-emphasised copy
   void* actA;              // conv ping
@@ -462,6 +465,7 @@ struct FrontWs {
   void* hbuf;              // (M,4096)
   float* feats;            // (M,1024) fp32
   int* ln_cnt;             // per 128-row block tile counters of the fused GEMM + LayerNorm (zeroed each forward)
+  float* partials;         // [<= 8][M][1024] K-split partial sums of out_proj / fc2 (streaming-chunk regime only)
 };
 
 static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_feats, Bump& b, FrontWs* w) {
@@ -478,6 +482,7 @@ static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_
   w->hbuf = b.take<char>((long long)d.M * 4096 * es);
   w->feats = own_feats ? b.take<float>((long long)d.M * 1024) : nullptr;
   w->ln_cnt = b.take<int>(d.M / 128 + 2);
+  w->partials = d.M <= kSkinnyRows ? b.take<float>(8LL * d.M * 1024) : nullptr;
 }
 
 struct AasistWs {
@@ -581,7 +586,6 @@ static bool posconv_slab_enabled() {
   return v == 1;
 }
 
-constexpr long long kSkinnyRows = 512;
 static bool skinny_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -607,11 +611,9 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
     if (variant == 256 && L.n % 256 == 0 && rows >= 2048 && gemm_2sm_enabled()) variant = 2256;   // CTA-pair tiles
     if (rows <= kSkinnyRows && L.n % 64 == 0 && skinny_enabled()) {
       // Streaming chunks (batch 1-8 x 49 frames, or one 4 s utterance): the GEMM is a weight-streaming problem, so
-      // the tile count -- not the tile shape -- sets the time.  64-wide tiles (4x the CTAs of the 256-wide ones)
-      // and split-K on the in-place residual GEMMs put (nearly) every SM on the weight stream.
-      TcEpilogue es = e;
-      es.k_splits = 0;
-      return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, es);
+      // the tile count -- not the tile shape -- sets the time: 64-wide tiles give 4x the CTAs of the 256-wide ones
+      // (the residual GEMMs of the transformer layers additionally split K, see run_frontend).
+      return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, e);
     }
     return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, variant, e);
   }
@@ -715,7 +717,30 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   }
   // transformer layers (pre-LN).  bf16 mode: every LayerNorm that follows a residual GEMM (LN2 after out_proj, the next
   // layer's LN1 / the final encoder LN after fc2) runs inside that GEMM as soon as a 128-row block is complete.
-  const bool fuse_ln = bf && fuse_ln_enabled();
+  const bool fuse_ln = bf && fuse_ln_enabled();   // opt-in: measured slower both at B=64 and for streaming chunks
+  // Streaming chunks: out_proj / fc2 (16 output tiles per 128 rows, K up to 4096) split K over the idle SMs; the partial
+  // sums land in w.partials and the LayerNorm that follows adds them to x in split order (deterministic).
+  const bool splitk = bf && !fuse_ln && !layer_taps && M <= kSkinnyRows && skinny_enabled() && w.partials;
+  const int sp_out = splitk ? tc_plan_splits(M, 1024, 1024) : 1, sp_fc2 = splitk ? tc_plan_splits(M, 1024, 4096) : 1;
+  int pending = 0;      // K-split partials of the previous residual GEMM not yet folded into x
+  auto layer_ln = [&](const Norm& n, float* of32, bf16* ob16) -> int {
+    if (pending > 1) {
+      const int np = pending;
+      pending = 0;
+      return layernorm_accum_rows(s, w.x, w.partials, np, M, n.g, n.b, 1e-5f, of32, ob16);
+    }
+    return layernorm_rows_f32(s, w.x, M, 1024, n.g, n.b, 1e-5f, ACT_NONE, of32, ob16);
+  };
+  auto residual_gemm = [&](const void* A, const Lin& L, int splits, TcEpilogue e) -> int {
+    if (splits > 1) {
+      TcEpilogue ep;
+      ep.bias = e.bias;
+      ep.partials = w.partials;
+      pending = splits;
+      return tc_gemm(s, plainA(A, M, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, ep);
+    }
+    return linear(c, s, A, M, L, e);
+  };
   if (fuse_ln) RTDF_CHECK_CUDA(cudaMemsetAsync(w.ln_cnt, 0, (size_t)(M / 128 + 2) * sizeof(int), s));
   const size_t n_layers = c->layers.size();
   const size_t tap_bytes = (size_t)M * 1024 * sizeof(float);
@@ -723,8 +748,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   for (size_t l = 0; l < n_layers; ++l) {
     const XlsrLayer& L = c->layers[l];
     if (l == 0 || !fuse_ln)
-      RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln1.g, L.ln1.b, 1e-5f, ACT_NONE,
-                                  bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
+      RTDF_TRY(layer_ln(L.ln1, bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
     {
       TcEpilogue e;
       e.bias = L.qkv.b;
@@ -752,11 +776,10 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       if (fuse_ln) {
         e.rowln_gamma = L.ln2.g; e.rowln_beta = L.ln2.b; e.rowln_out_bf16 = static_cast<bf16*>(w.xb); e.rowln_counters = w.ln_cnt;
       }
-      RTDF_TRY(linear(c, s, w.attn, M, L.out, e));
+      RTDF_TRY(residual_gemm(w.attn, L.out, sp_out, e));
     }
     if (!fuse_ln)
-      RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, L.ln2.g, L.ln2.b, 1e-5f, ACT_NONE,
-                                  bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
+      RTDF_TRY(layer_ln(L.ln2, bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
     {
       TcEpilogue e;
       e.bias = L.fc1.b;
@@ -781,13 +804,12 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
           e.rowln_gamma = c->enc_ln.g; e.rowln_beta = c->enc_ln.b; e.rowln_out_f32 = feats;
         }
       }
-      RTDF_TRY(linear(c, s, w.hbuf, M, L.fc2, e));
+      RTDF_TRY(residual_gemm(w.hbuf, L.fc2, sp_fc2, e));
     }
     if (layer_taps)   // output of encoder.layers[l] (the KD hook point, trainer.py:176-195)
       RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps + (l + 1) * (size_t)M * 1024, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
   }
-  if (!fuse_ln)
-    RTDF_TRY(layernorm_rows_f32(s, w.x, M, 1024, c->enc_ln.g, c->enc_ln.b, 1e-5f, ACT_NONE, feats, nullptr));
+  if (!fuse_ln) RTDF_TRY(layer_ln(c->enc_ln, feats, nullptr));
   return RTDF_OK;
 }
 
@@ -1242,6 +1264,7 @@ int rtdf_forward(rtdf_ctx* c, const float* wav, int B, int N, int preemph_on, fl
   RTDF_REQUIRE(b.off <= ws_bytes, "rtdf_forward: workspace too small (%zu < %zu bytes)", ws_bytes, b.off);
   RTDF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "rtdf_forward: workspace must be 256-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pdl_set_auto(d.M <= kPdlRows);
   RTDF_TRY(run_frontend(c, s, wav, d, preemph_on, coef, fw, fw.feats, taps ? taps->layers : nullptr));
   if (taps && taps->feats)
     RTDF_CHECK_CUDA(cudaMemcpyAsync(taps->feats, fw.feats, (size_t)d.M * 1024 * 4, cudaMemcpyDeviceToDevice, s));
@@ -1260,6 +1283,7 @@ int rtdf_frontend(rtdf_ctx* c, const float* wav, int B, int N, int preemph_on, f
   plan_front(c, d, preemph_on != 0, false, b, &fw);
   RTDF_REQUIRE(b.off <= ws_bytes, "rtdf_frontend: workspace too small (%zu < %zu bytes)", ws_bytes, b.off);
   RTDF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "rtdf_frontend: workspace must be 256-byte aligned");
+  pdl_set_auto(d.M <= kPdlRows);
   return run_frontend(c, static_cast<cudaStream_t>(stream), wav, d, preemph_on, coef, fw, feats);
 }
 
@@ -1274,6 +1298,7 @@ int rtdf_backend(rtdf_ctx* c, const float* feats, int B, int T, float* logits, v
   backend_plan(c, B, T, b, &aw, &cw);
   RTDF_REQUIRE(b.off <= ws_bytes, "rtdf_backend: workspace too small (%zu < %zu bytes)", ws_bytes, b.off);
   RTDF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "rtdf_backend: workspace must be 256-byte aligned");
+  pdl_set_auto((long long)B * T <= kPdlRows);
   return run_backend(c, static_cast<cudaStream_t>(stream), feats, B, T, logits, taps, aw, cw);
 }
 

@@ -16,13 +16,19 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// Programmatic dependent launch: RTDF_PDL=0/1 forces it off/on; otherwise the forward turns it on for small
+// problems (streaming chunks), where kernels last a few microseconds and overlapping the next kernel's prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) with the current kernel's tail is worth ~5 % of the latency.
+// At batch 64 it measured 2.5 % slower inside the CUDA graph (r01), so large problems keep plain stream order.
+static int g_pdl_auto = 0;
+void pdl_set_auto(bool on) { g_pdl_auto = on ? 1 : 0; }
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("RTDF_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;   // measured on B200 (r01): the attribute costs ~2.5 % end to end, so it is opt-in
+    forced = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
   }
-  return v == 1;
+  return forced >= 0 ? forced == 1 : g_pdl_auto == 1;
 }
 
 static long long g_launches = 0;

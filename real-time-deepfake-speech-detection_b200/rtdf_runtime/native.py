@@ -53,6 +53,10 @@ SIGNATURES = {
     "rtdf_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rtdf_gemm_bf16_rowln": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rtdf_gemm_plan_splits": (c_int, [c_int, c_int, c_int]),
+    "rtdf_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rtdf_layernorm_accum_rows": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_float, c_void_p,
+                                          c_void_p, c_void_p]),
     "rtdf_gemm_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "rtdf_conv1d_ln_gelu_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p]),
     "rtdf_posconv_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),

@@ -157,23 +157,43 @@ def check_gemm_bf16(variants=(64, 128, 256)):
 
 
 def check_gemm_splitk():
-    """Skinny in-place residual GEMMs (streaming chunks): 64-wide tiles with split-K, partials met by TMA reduce-add."""
+    """Skinny residual GEMM + LayerNorm of the streaming-chunk regime: K split over idle SMs, partial sums folded into
+    the residual stream in split order by the LayerNorm that follows (bit-reproducible)."""
+    from tests.util import native
+    lib = native().load()
     g = torch.Generator().manual_seed(13)
     out = {}
-    for M, N, K in ((49, 1024, 4096), (49, 1024, 1024), (199, 1024, 4096), (392, 1024, 1024), (8, 128, 1024), (49, 64, 128)):
+    assert lib.rtdf_gemm_plan_splits(12736, 1024, 4096) == 1          # large batch: never split
+    for M, K in ((49, 4096), (49, 1024), (199, 4096), (392, 1024), (8, 1024), (500, 4096)):
+        N = 1024
+        S = lib.rtdf_gemm_plan_splits(M, N, K)
+        assert 2 <= S <= 8, (M, K, S)
         A = (torch.randn(M, K, generator=g)).to(torch.bfloat16)
         W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
         b = torch.randn(N, generator=g)
-        R = torch.randn(M, N, generator=g)
-        ref = (A.float() @ W.float().t() + b) * 0.5 + R
-        o = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=0, scale=0.5, resid=R.to(DEV), variant=1064, inplace=True)
-        d = float((o.cpu() - ref).abs().max())
-        out[f"{M}x{N}x{K}"] = d
-        assert d <= 2e-3, out
-        # with an activation the call must fall back to a single split and still be right
-        o2 = gemm_bf16(A.to(DEV), W.to(DEV), b.to(DEV), act=1, scale=1.0, resid=R.to(DEV), variant=1064, inplace=True)
-        d2 = float((o2.cpu() - (F.gelu(A.float() @ W.float().t() + b) + R)).abs().max())
-        assert d2 <= 2e-3, (out, d2)
+        x0 = torch.randn(M, N, generator=g) * 2
+        gamma = 1 + 0.1 * torch.randn(N, generator=g)
+        beta = 0.1 * torch.randn(N, generator=g)
+        xr = x0 + A.float() @ W.float().t() + b
+        ref = F.layer_norm(xr, (N,), gamma, beta, 1e-5)
+        runs = []
+        for rep in range(3):
+            parts = torch.full((S, M, N), float("nan"), device=DEV)
+            x = x0.to(DEV)
+            o16 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+            call("rtdf_gemm_bf16_splitk", P(dev(A)), P(dev(W)), M, N, K, P(dev(b)), P(parts), stream())
+            call("rtdf_layernorm_accum_rows", P(x), P(parts), S, M, P(dev(gamma)), P(dev(beta)), 1e-5, None, P(o16), stream())
+            x2 = x0.to(DEV)
+            o32 = torch.empty(M, N, device=DEV)
+            call("rtdf_layernorm_accum_rows", P(x2), P(parts), S, M, P(dev(gamma)), P(dev(beta)), 1e-5, P(o32), None, stream())
+            runs.append((x.cpu(), o16.cpu(), o32.cpu()))
+        dx = float((runs[0][0] - xr).abs().max())
+        d32 = float((runs[0][2] - ref).abs().max())
+        d16 = float((runs[0][1].float() - ref).abs().max())
+        out[f"{M}x{N}x{K}_S{S}"] = (dx, d32, d16)
+        assert dx <= 2e-3 and d32 <= 2e-3 and d16 <= 0.04, out
+        for r in runs[1:]:           # bit-reproducible: no atomics, fixed summation order
+            assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
     return out
 
 

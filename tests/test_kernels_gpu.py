@@ -37,11 +37,11 @@ def test_gemm_bf16_tcgen05(variant):
     kc.check_gemm_bf16(variants=(variant,))
 
 
-def test_gemm_split_k_reduce_add():
+def test_gemm_split_k_partials_and_accumulating_layernorm():
     kc.check_gemm_splitk()
 
 
-@pytest.mark.parametrize("variant", [256, 2256])
+@pytest.mark.parametrize("variant", [256, 2256, 64])
 def test_gemm_with_fused_row_layernorm(variant):
     kc.check_gemm_rowln(variants=(variant,))
 

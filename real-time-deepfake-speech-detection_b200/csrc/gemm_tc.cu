@@ -33,6 +33,7 @@ struct TcKernelParams {
   int tiles_n, tiles_m, total_tiles;
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
   int epi_mode;
+  int debug = 0;           // RTDF_GEMM_DEBUG bit mask (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
   int k_splits = 1;        // split-K: tile t covers k-blocks [split * kb_per_split, ...) and reduce-adds its partial
   int kb_per_split = 0;
   TcEpilogue epi;
@@ -639,6 +640,10 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
+          if (p.debug & 1) {             // timing experiment: operands are whatever the shared memory holds
+            if (leader) mbar_arrive(full_bar(s));
+            continue;
+          }
           if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
           const uint32_t full_leader = mapa_shared(full_bar(s), 0);
           const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
@@ -665,9 +670,11 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_base + s * Cfg::kStageBytes;
           const uint32_t b_addr = a_addr + Cfg::kABytes;
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            mma_bf16_ss_2sm(d_tmem, make_desc(a_addr + k * 32, BK), make_desc(b_addr + k * 32, BK), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              mma_bf16_ss_2sm(d_tmem, make_desc(a_addr + k * 32, BK), make_desc(b_addr + k * 32, BK), idesc, (kb | k) != 0);
+          }
           mma_commit_2sm(empty_bar(s), 3);   // both CTAs' smem slots
         }
         mma_commit_2sm(tfull_bar(a), 3);     // both CTAs' accumulator halves
@@ -699,7 +706,8 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       __syncwarp();
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
+      if (!(p.debug & 4))
+        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
@@ -1121,6 +1129,14 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   p.epi = epi;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, false, 256));
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("RTDF_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_2sm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
   ProfRec rec{};

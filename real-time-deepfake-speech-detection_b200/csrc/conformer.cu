@@ -1,6 +1,8 @@
 // Conformer back-end kernels (fp32 arithmetic, fp32 or bf16 I/O).
 #include "conformer.cuh"
 
+#include <stdlib.h>
+
 namespace rtdf {
 
 __global__ void conformer_stem_kernel(const float* __restrict__ z, const float* __restrict__ tok, int T, int E,
@@ -112,6 +114,15 @@ int conformer_attention_f32(cudaStream_t s, const float* qkv, const float* rel_p
   return attn_launch<float>(s, qkv, rel_pos, out, B, n, heads, dh);
 }
 int conformer_attention_bf16(cudaStream_t s, const bf16* qkv, const float* rel_pos, bf16* out, int B, int n, int heads, int dh) {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("RTDF_CONF_ATTN_IMPL");
+    impl = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (impl == 0) {
+    const int r = conformer_attention_mma(s, qkv, rel_pos, out, B, n, heads, dh);
+    if (r != RTDF_ERR_UNSUPPORTED) return r;
+  }
   return attn_launch<bf16>(s, qkv, rel_pos, out, B, n, heads, dh);
 }
 
@@ -161,11 +172,68 @@ glu_dwconv_kernel(const T_* __restrict__ in, T_* __restrict__ out, int n, int in
   }
 }
 
+// Same contract with the tap count known at compile time: every thread (= channel) produces 8 consecutive time steps
+// per pass from K + 7 shared-memory reads (6.5 FMAs per LDS instead of 1), 64 time steps per CTA.
+constexpr int kDwTT2 = 64;
+template <typename T_, int K>
+__global__ void __launch_bounds__(512)
+glu_dwconv_k_kernel(const T_* __restrict__ in, T_* __restrict__ out, int n, int inner, const float* __restrict__ w,
+                    const float* __restrict__ bias, const float* __restrict__ bn_s, const float* __restrict__ bn_t) {
+  extern __shared__ float tile[];  // [kDwTT2 + K - 1][inner]
+  const int b = blockIdx.y, t0 = blockIdx.x * kDwTT2;
+  constexpr int padl = K / 2;
+  constexpr int rows = kDwTT2 + K - 1;
+  const T_* inb = in + (long long)b * n * 2 * inner;
+  for (int i = threadIdx.x; i < rows * inner; i += blockDim.x) {
+    const int r = i / inner, c = i % inner;
+    const int t = t0 - padl + r;
+    float v = 0.f;
+    if (t >= 0 && t < n) {
+      const float a = to_f32(inb[(long long)t * 2 * inner + c]);
+      const float g = to_f32(inb[(long long)t * 2 * inner + inner + c]);
+      v = a * sigmoid_f(g);
+    }
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= inner) return;
+  float wk[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wk[j] = w[c * K + j];
+  const float bi = bias[c], sc = bn_s[c], sh = bn_t[c];
+  for (int tt0 = 0; tt0 < kDwTT2 && t0 + tt0 < n; tt0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = bi;
+#pragma unroll
+    for (int j = 0; j < K + 7; ++j) {
+      const float v = tile[(tt0 + j) * inner + c];
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (j - o >= 0 && j - o < K) acc[o] = fmaf(wk[j - o], v, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int t = t0 + tt0 + o;
+      if (t < n) out[((long long)b * n + t) * inner + c] = from_f32<T_>(swish_f(acc[o] * sc + sh));
+    }
+  }
+}
+
 template <typename T_>
 static int dw_launch(cudaStream_t s, const T_* in, T_* out, int B, int n, int inner, int k, const float* w,
                      const float* bias, const float* bn_s, const float* bn_t) {
   RTDF_REQUIRE(in && out && w && bias && bn_s && bn_t, "glu_dwconv: bad arguments");
   RTDF_REQUIRE(k % 2 == 1 && k <= kDwMaxK && inner <= 512, "glu_dwconv: unsupported kernel %d / width %d", k, inner);
+  if (k == 31 && (size_t)(kDwTT2 + 30) * inner * sizeof(float) <= 200 * 1024) {      // the reference's kernel_size
+    const size_t smem2 = (size_t)(kDwTT2 + 30) * inner * sizeof(float);
+    RTDF_CHECK_CUDA(cudaFuncSetAttribute(glu_dwconv_k_kernel<T_, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    glu_dwconv_k_kernel<T_, 31><<<dim3(ceil_div(n, kDwTT2), B), ((inner + 31) / 32) * 32, smem2, s>>>(in, out, n, inner, w, bias,
+                                                                                                     bn_s, bn_t);
+    RTDF_LAUNCH_CHECK();
+    return RTDF_OK;
+  }
   const size_t smem = (size_t)(kDwTT + k - 1) * inner * sizeof(float);
   RTDF_REQUIRE(smem <= 200 * 1024, "glu_dwconv: tile too large");
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(glu_dwconv_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

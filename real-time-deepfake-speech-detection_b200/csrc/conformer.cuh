@@ -15,6 +15,10 @@ int conformer_stem(cudaStream_t s, const float* z, const float* class_token, int
 int conformer_attention_f32(cudaStream_t s, const float* qkv, const float* rel_pos, float* out, int B, int n, int heads, int dh);
 int conformer_attention_bf16(cudaStream_t s, const bf16* qkv, const float* rel_pos, bf16* out, int B, int n, int heads, int dh);
 
+// Same contract on the tensor cores (conformer_attn_mma.cu; bf16, n <= 208, dh <= 40 even); RTDF_ERR_UNSUPPORTED outside
+// that envelope.  conformer_attention_bf16 uses it when it applies (RTDF_CONF_ATTN_IMPL=1 forces the SIMT kernel).
+int conformer_attention_mma(cudaStream_t s, const bf16* qkv, const float* rel_pos, bf16* out, int B, int n, int heads, int dh);
+
 // in: (B*n, 2*inner) pointwise-conv output; out (B*n, inner) = Swish(BN(depthwise_k(GLU(in)) + bias))
 int conformer_glu_dwconv_f32(cudaStream_t s, const float* in, float* out, int B, int n, int inner, int k,
                              const float* w, const float* bias, const float* bn_s, const float* bn_t);

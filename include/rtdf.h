@@ -129,7 +129,8 @@ int rtdf_gemm_f32(const float* A, const float* W, int M, int N, int K, const flo
                   const float* resid, float* out_f32, void* stream);
 /* Strided 1-D conv as implicit GEMM on channels-last bf16 activations, fused bias + LayerNorm(512) + GELU:
  * x (B, L_in, 512) -> y (B, L_out, 512), w packed [512][k][512] bf16.  variant 512 (BK 64) | 513 (BK 32): single
- * 512-column accumulator; 514 (BK 32) | 515 (BK 64): pipelined two-pass tile with 16 epilogue warps. */
+ * 512-column accumulator; 514 (BK 32) | 515 (BK 64): pipelined two-pass tile with 16 epilogue warps; 516: the same
+ * as a CTA pair (cta_group::2, 256 rows per cluster: half the weight stream per output row). */
 int rtdf_conv1d_ln_gelu_bf16(const void* x, int batch, int l_in, int k, int stride, const void* w_packed,
                              const float* bias, const float* gamma, const float* beta, float eps, void* y,
                              int variant, void* stream);

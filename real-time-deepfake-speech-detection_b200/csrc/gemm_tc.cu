@@ -966,6 +966,250 @@ tc_conv_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+// =================================================================================================
+// CTA-pair (cta_group::2) version of the pipelined full-row LayerNorm tile: a 2-CTA cluster owns 256 rows x 512 columns.
+// The single-CTA kernel streams the whole weight matrix (512 x K) plus the A tile twice per 128 rows -- 2.3 MB per tile
+// for conv-1 (K = 1536), 7.4 GB per launch at B = 64, i.e. L2-bandwidth bound (615 us at ~12 TB/s; measured 600 us).
+// Here every CTA loads its 128 A rows and only ITS HALF of the 256 W rows of a pass; the leader issues M = 256 MMAs, so
+// the weight traffic per output row halves.  Barrier protocol as in tc_gemm_2sm_kernel; epilogue as in
+// tc_conv_ln_kernel (each CTA normalises its own 128 rows).
+// =================================================================================================
+template <int BK>
+struct TcLn2Cfg {
+  static constexpr int kEpiWarps = 16;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = 128 * BK * 2;              // this CTA's half of the 256 W rows of a pass
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;
+  static constexpr int kParamBytes = 3 * 512 * 4 + 2 * 4 * 128 * 8;     // bias|gamma|beta + stats[2][4][128] float2
+  static constexpr int kFixed = kStagingBytes + 256 + kParamBytes;
+  static constexpr int kStagesRaw = (kMaxSmem - 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed + 1024;
+};
+
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TcLn2Cfg<BK>::kThreads, 1)
+tc_conv_ln_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapC, const TcKernelParams p) {
+  using Cfg = TcLn2Cfg<BK>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiThreads = Cfg::kEpiWarps * 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int kOffStaging = kStages * Cfg::kStageBytes;
+  constexpr int kOffBars = kOffStaging + Cfg::kStagingBytes;
+  constexpr int kOffParams = kOffBars + 256;
+  const uint32_t bar_base = smem_base + kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int h) { return bar_base + 8u * (2 * kStages + h); };
+  auto tempty_bar = [&](int h) { return bar_base + 8u * (2 * kStages + 2 + h); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kOffBars + 8 * (2 * kStages + 4));
+  float* s_params = reinterpret_cast<float*>(smem_gen + kOffParams);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    prefetch_tmap(&mapC);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(tfull_bar(h), 1);
+      mbar_init(tempty_bar(h), 2 * Cfg::kEpiWarps);  // one elected arrive per epilogue warp of both CTAs (leader's copy)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  for (int i = threadIdx.x; i < 512; i += Cfg::kThreads) {
+    s_params[i] = p.epi.bias ? p.epi.bias[i] : 0.f;
+    s_params[512 + i] = p.epi.ln_gamma[i];
+    s_params[1024 + i] = p.epi.ln_beta[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int total_m = p.total_tiles;                 // 256-row pair tiles x batches
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int t = pair; t < total_m; t += n_pairs) {
+        const int m_tile = t % p.tiles_m, batch = t / p.tiles_m;
+        const int m0 = m_tile * 256 + (int)rank * 128;
+        for (int h = 0; h < 2; ++h)
+          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+            const uint32_t full_leader = mapa_shared(full_bar(s), 0);
+            const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
+            tma_load_3d_2sm(a_dst, &mapA, full_leader, kb * BK, m0, batch);
+            tma_load_2d_2sm(a_dst + Cfg::kABytes, &mapB, full_leader, kb * BK, h * 256 + (int)rank * 128);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (leader CTA only): M = 256 over the pair =====
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+      uint32_t it = 0, lt = 0;
+      for (int t = pair; t < total_m; t += n_pairs, ++lt) {
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(tempty_bar(h), (lt & 1) ^ 1);     // half h of the previous tile has been normalised and stored
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + h * 256;
+          for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base + s * Cfg::kStageBytes;
+            const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              mma_bf16_ss_2sm(d_tmem, make_desc(a_addr + k * 32, BK), make_desc(b_addr + k * 32, BK), idesc, (kb | k) != 0);
+            mma_commit_2sm(empty_bar(s), 3);
+          }
+          mma_commit_2sm(tfull_bar(h), 3);
+        }
+      }
+      pdl_launch_dependents();
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp & 3;
+    const int j = (warp - 2) >> 2;
+    uint8_t* box_gen = smem_gen + kOffStaging + (warp - 2) * 4096;
+    const uint32_t box = smem_base + kOffStaging + (warp - 2) * 4096;
+    const float* s_bias = s_params;
+    const float* s_gamma = s_params + 512;
+    const float* s_beta = s_params + 1024;
+    float2* s_stat_all = reinterpret_cast<float2*>(s_params + 1536);      // [2][4][128]
+    const int act = p.epi.act;
+    uint32_t lt = 0;
+    for (int t = pair; t < total_m; t += n_pairs, ++lt) {
+      const int m_tile = t % p.tiles_m, batch = t / p.tiles_m;
+      const int row0 = m_tile * 256 + (int)rank * 128 + q * 32;
+      const uint32_t tph = lt & 1;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      float2* s_stat = s_stat_all + (lt & 1) * 512;
+      // ---- pass 1: row statistics of this warp's 64 + 64 columns (half 0 while the tensor pipe fills half 1) ----
+      float2 sum2 = make_float2(0.f, 0.f), ssq2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(tfull_bar(h), tph);
+        __syncwarp();
+        tc_fence_after();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = h * 256 + j * 64 + sub * 32;
+          uint32_t r[32];
+          tmem_ld32(t_row + c, r);
+          tmem_ld_wait();
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 v = add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]);
+            sum2 = add2(sum2, v);
+            ssq2 = fma2(v, v, ssq2);
+          }
+        }
+      }
+      s_stat[j * 128 + q * 32 + lane] = make_float2(sum2.x + sum2.y, ssq2.x + ssq2.y);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      float sum = 0.f, ssq = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float2 o = s_stat[jj * 128 + q * 32 + lane];
+        sum += o.x;
+        ssq += o.y;
+      }
+      const float mean = sum * (1.0f / 512.0f);
+      const float var = fmaxf(ssq * (1.0f / 512.0f) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.epi.ln_eps);
+      const float2 rstd2 = make_float2(rstd, rstd), nmean2 = make_float2(-mean, -mean);
+      // ---- pass 2: normalise / GELU / store, half 0 first so that the next tile's MMAs can start on it ----
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = h * 256 + j * 64;
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = c0 + sub * 32;
+          uint32_t r[32];
+          tmem_ld32(t_row + c, r);
+          tmem_ld_wait();
+          __align__(8) float o[32];
+          float2* o2 = reinterpret_cast<float2*>(o);
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c);
+          const float2* g2 = reinterpret_cast<const float2*>(s_gamma + c);
+          const float2* be2 = reinterpret_cast<const float2*>(s_beta + c);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 v = add2(add2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]), nmean2);
+            o2[i] = fma2(v, mul2(g2[i], rstd2), be2[i]);
+          }
+          if (act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o2[i] = gelu2(o2[i]);
+          } else if (act == ACT_GELU_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o2[i] = gelu2_tanh(o2[i]);
+          } else if (act == ACT_GELU_AS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = gelu_fast(o[i]);
+          }
+          // 32 bf16 = 64 bytes = chunks 4*sub .. 4*sub+3 of this lane's 128-byte box row (SWIZZLE_128B)
+          uint8_t* rowp = box_gen + lane * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(rowp + (((4 * sub + ch) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16x2(o[8 * ch], o[8 * ch + 1]), pack_bf16x2(o[8 * ch + 2], o[8 * ch + 3]),
+                           pack_bf16x2(o[8 * ch + 4], o[8 * ch + 5]), pack_bf16x2(o[8 * ch + 6], o[8 * ch + 7]));
+        }
+        // all TMEM reads of half h by this warp are complete: hand it back to the MMA warp
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_shared(tempty_bar(h), 0));
+          if (row0 < p.rows_per_batch) {
+            tma_store_3d(&mapC, box, c0, row0, batch);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();            // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 static int g_gelu_override = 0;
 int tc_get_gelu_variant() { return g_gelu_override; }
 void tc_set_gelu_variant(int act) { g_gelu_override = (act == ACT_GELU_TANH || act == ACT_GELU_AS) ? act : 0; }
@@ -1209,6 +1453,58 @@ static int launch_conv_ln(cudaStream_t stream, const TcOperandA& A, const bf16* 
   return RTDF_OK;
 }
 
+template <int BK>
+static int launch_conv_ln_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int Kw, const TcEpilogue& epi) {
+  using Cfg = TcLn2Cfg<BK>;
+  static_assert(Cfg::kStages >= 3, "need at least three stages");
+  static_assert(8 * (2 * Cfg::kStages + 5) <= 256, "barrier block too small");
+  const int N = 512;
+  CUtensorMap mapA, mapB, mapC;
+  {
+    uint64_t dims[3] = {(uint64_t)A.k_extent, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
+    uint64_t strides[2] = {(uint64_t)A.row_stride * 2, (uint64_t)(A.batches > 1 ? A.batch_stride : A.row_stride * A.rows_per_batch) * 2};
+    uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
+    RTDF_TRY(make_tmap_bf16(&mapA, A.ptr, 3, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)Kw * 2};
+    uint32_t box[2] = {(uint32_t)BK, 128};
+    RTDF_TRY(make_tmap_bf16(&mapB, W, 2, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
+  }
+  TcKernelParams p;
+  p.rows_per_batch = (int)A.rows_per_batch;
+  p.N = N;
+  p.num_kb = ceil_div(Kw, BK);
+  p.tiles_n = 1;
+  p.tiles_m = ceil_div((int)A.rows_per_batch, 256);
+  const long long total = (long long)p.tiles_m * A.batches;
+  RTDF_REQUIRE(total < (1LL << 31), "tc_gemm: too many tiles");
+  p.total_tiles = (int)total;
+  p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
+  p.epi = epi;
+  if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
+  RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, true, 512));
+  RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_ln_2sm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int grid = 2 * (p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2);
+  ProfRec rec{};
+  if (g_prof_on) {
+    RTDF_CHECK_CUDA(cudaEventCreate(&rec.a));
+    RTDF_CHECK_CUDA(cudaEventCreate(&rec.b));
+    rec.flops = 2.0 * (double)A.rows_per_batch * (double)A.batches * (double)N * (double)Kw;
+    rec.variant = 516;
+    RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
+  }
+  RTDF_CHECK_CUDA(launch_pdl(tc_conv_ln_2sm_kernel<BK>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, mapA, mapB,
+                             mapC, p));
+  RTDF_LAUNCH_CHECK();
+  if (g_prof_on) {
+    RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    g_prof.push_back(rec);
+  }
+  return RTDF_OK;
+}
+
 int tc_plan_splits(long long rows, int N, int Kw) {
   const long long tiles = ((rows + BM - 1) / BM) * ((N + 63) / 64);
   const int num_kb = (Kw + 63) / 64;
@@ -1241,6 +1537,9 @@ int tc_gemm(cudaStream_t stream, const TcOperandA& A, const bf16* W, int N, int 
     case 515:
       RTDF_REQUIRE(N == 512 && epi.ln_gamma && epi.ln_beta && mode == TC_PLAIN, "tc_gemm: LN variant needs N == 512 and LN parameters");
       return variant == 514 ? launch_conv_ln<32>(stream, A, W, Kw, epi) : launch_conv_ln<64>(stream, A, W, Kw, epi);
+    case 516:   // CTA-pair version of the pipelined LayerNorm tile
+      RTDF_REQUIRE(N == 512 && epi.ln_gamma && epi.ln_beta && mode == TC_PLAIN, "tc_gemm: LN variant needs N == 512 and LN parameters");
+      return launch_conv_ln_2sm<64>(stream, A, W, Kw, epi);
     case 512:
     case 513:
       RTDF_REQUIRE(N == 512 && epi.ln_gamma && epi.ln_beta, "tc_gemm: LN variant needs N == 512 and LN parameters");

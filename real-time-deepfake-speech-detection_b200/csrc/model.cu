@@ -595,6 +595,15 @@ static bool skinny_enabled() {
   return v == 1;
 }
 
+static bool conv_2sm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_CONV_2SM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool fuse_ln_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -652,7 +661,10 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       e.ln_beta = f.ln.b;
       e.out_bf16 = static_cast<bf16*>(nxt);
       e.ld_bf16 = 512;
-      RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, 515, e));   // pipelined two-pass LN tile
+      // pipelined two-pass LayerNorm tile.  The CTA pair halves the weight stream per output row: +5 % on conv-1
+      // (561 vs 592 us at B = 64), a tie on conv-2 and a loss on the short layers, so it is used for long outputs only.
+      const int variant = conv_2sm_enabled() && (long long)B * Lout >= 200000 ? 516 : 515;
+      RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, variant, e));
     } else {
       SimtOperandA a;
       a.ptr = static_cast<const float*>(cur);
@@ -757,7 +769,9 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       RTDF_TRY(linear(c, s, w.xb, M, L.qkv, e));
     }
     if (bf) {
-      if (c->d.attention_impl == 0)
+      if (T > 256)   // beyond the tcgen05 kernels' single key tile (5.1 s of audio): SIMT kernel, K / V of a head in smem
+        RTDF_TRY(attention_simt_bf16(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
+      else if (c->d.attention_impl == 0)
         RTDF_TRY(attention_ws(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
       else if (c->d.attention_impl == 2)
         RTDF_TRY(attention_tc(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));

@@ -49,6 +49,13 @@ def test_ragged_batches_preemphasis_determinism():
     ec.check_ragged_and_quirks(precision="fp32")
 
 
+def test_utterances_longer_than_one_attention_tile():
+    """T > 256 frames (> 5.1 s): the transformer falls back to the smem-resident SIMT attention; the AASIST back-end
+    reaches 290 frames, the Conformer ~400 (beyond that the call raises, see test_errors_are_loud)."""
+    ec.check_e2e("My_XLSR_AASIST", "bf16", B=1, N=88000, num_layers=2, order="first")       # 5.5 s, T = 274
+    ec.check_e2e("MyModel", "bf16", B=1, N=100000, num_layers=2, fixed_call=True)            # 6.25 s, T = 312
+
+
 def test_errors_are_loud():
     import torch
     from tests.util import build_pair

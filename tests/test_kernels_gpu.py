@@ -50,7 +50,7 @@ def test_gelu_epilogue_accuracy():
     kc.check_gelu_epilogue()
 
 
-@pytest.mark.parametrize("variant", [512, 513, 514, 515])
+@pytest.mark.parametrize("variant", [512, 513, 514, 515, 516])
 def test_conv1d_implicit_gemm_ln_gelu(variant):
     kc.check_conv1d_tc(variants=(variant,))
 

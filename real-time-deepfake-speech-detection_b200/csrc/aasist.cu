@@ -374,7 +374,7 @@ static int gat_launch(cudaStream_t s, const GraphView& x, int B, int n1, const G
                       long long out_bs, const float* master_in, long long master_stride, const GatRowWeights* wM,
                       float* master_out) {
   const size_t smem = ((size_t)kMaxNodes * D + DO * (D + 4) + 4 * DO + kMaxNodes + 2 * D) * sizeof(float);
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(gat_rows_kernel<D, DO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&gat_rows_kernel<D, DO>), (size_t)smem));
   const bool has_master = master_in != nullptr;
   dim3 grid(x.n + (has_master ? 1 : 0), B);
   gat_rows_kernel<D, DO><<<grid, 256, smem, s>>>(x, n1, w, out, out_bs, master_in, master_stride,

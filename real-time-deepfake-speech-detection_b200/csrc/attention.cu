@@ -428,7 +428,7 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   uint32_t boxkv[3] = {64, (uint32_t)p.Tk, 1};
   RTDF_TRY(make_tmap_bf16(&mapQ, qkv, 3, dims, strides, boxq, TMAP_SW128));
   RTDF_TRY(make_tmap_bf16(&mapKV, qkv, 3, dims, strides, boxkv, TMAP_SW128));
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_ws_kernel), (size_t)smem));
   const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
   RTDF_CHECK_CUDA(launch_pdl(attention_ws_kernel, dim3(grid), dim3(kWsThreads), smem, s, mapQ, mapKV, ctx, p));
   RTDF_LAUNCH_CHECK();
@@ -507,7 +507,7 @@ static int simt_launch(cudaStream_t s, const T_* qkv, T_* ctx, int B, int T, int
   const int Tp = (T + 31) & ~31;
   const size_t smem = ((size_t)T * 65 + (size_t)T * 64 + 8 * 64 + 8 * Tp) * sizeof(float);
   RTDF_REQUIRE(smem <= 220 * 1024, "attention_simt: T = %d too long for the smem-resident K/V kernel", T);
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_simt_kernel<T_>), (size_t)smem));
   dim3 grid(B * H, ceil_div(T, kSimtQPerCta));
   attention_simt_kernel<T_><<<grid, 256, smem, s>>>(qkv, ctx, T, H);
   RTDF_LAUNCH_CHECK();

@@ -83,6 +83,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
+// Opt-in dynamic shared memory of a kernel whose request varies from launch to launch: the per-function limit is only ever
+// RAISED (per device).  Lowering it between launches is legal for plain launches but breaks tools that re-launch the kernel
+// nodes of a captured CUDA graph with the function's current attributes (ncu: LaunchFailed on the node that needs more).
+cudaError_t raise_max_dyn_smem(const void* func, size_t bytes);
+
 constexpr int kNumSMs = 148;  // B200
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -104,7 +104,7 @@ static int attn_launch(cudaStream_t s, const T_* qkv, const float* rel, T_* out,
   const int np = (n + 31) & ~31;
   const size_t smem = ((size_t)n * (dh + 1) + (size_t)n * dh + (size_t)(2 * n - 1) * (dh + 1) + 8 * 64 + 8 * np) * sizeof(float);
   RTDF_REQUIRE(smem <= 220 * 1024, "conformer_attention: sequence of %d tokens too long", n);
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(conformer_attn_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&conformer_attn_kernel<T_>), (size_t)smem));
   dim3 grid(B * heads, ceil_div(n, 32));
   conformer_attn_kernel<T_><<<grid, 256, smem, s>>>(qkv, rel, out, n, heads, dh, 1.0f / sqrtf((float)dh));
   RTDF_LAUNCH_CHECK();
@@ -228,7 +228,7 @@ static int dw_launch(cudaStream_t s, const T_* in, T_* out, int B, int n, int in
   RTDF_REQUIRE(k % 2 == 1 && k <= kDwMaxK && inner <= 512, "glu_dwconv: unsupported kernel %d / width %d", k, inner);
   if (k == 31 && (size_t)(kDwTT2 + 30) * inner * sizeof(float) <= 200 * 1024) {      // the reference's kernel_size
     const size_t smem2 = (size_t)(kDwTT2 + 30) * inner * sizeof(float);
-    RTDF_CHECK_CUDA(cudaFuncSetAttribute(glu_dwconv_k_kernel<T_, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&glu_dwconv_k_kernel<T_, 31>), (size_t)smem2));
     glu_dwconv_k_kernel<T_, 31><<<dim3(ceil_div(n, kDwTT2), B), ((inner + 31) / 32) * 32, smem2, s>>>(in, out, n, inner, w, bias,
                                                                                                      bn_s, bn_t);
     RTDF_LAUNCH_CHECK();
@@ -236,7 +236,7 @@ static int dw_launch(cudaStream_t s, const T_* in, T_* out, int B, int n, int in
   }
   const size_t smem = (size_t)(kDwTT + k - 1) * inner * sizeof(float);
   RTDF_REQUIRE(smem <= 200 * 1024, "glu_dwconv: tile too large");
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(glu_dwconv_kernel<T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&glu_dwconv_kernel<T_>), (size_t)smem));
   const int threads = ((inner + 31) / 32) * 32;
   glu_dwconv_kernel<T_><<<dim3(ceil_div(n, kDwTT), B), threads, smem, s>>>(in, out, n, inner, k, w, bias, bn_s, bn_t);
   RTDF_LAUNCH_CHECK();

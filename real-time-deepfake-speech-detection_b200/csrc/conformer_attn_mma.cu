@@ -185,7 +185,7 @@ template <int NT>
 int launch(cudaStream_t s, const bf16* qkv, const float* rel, bf16* out, int B, int n, int heads, int dh) {
   constexpr int NK = NT * 8, VS = NK + 8, QES = (NK + 16 + 31) / 32 * 32 + 8;
   const size_t smem = (size_t)(NK * kDP + (2 * NK + 16) * kDP + kDP * VS) * sizeof(bf16) + (size_t)kWarps * 16 * QES * sizeof(float);
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(conformer_attn_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&conformer_attn_mma_kernel<NT>), (size_t)smem));
   const int n_qt = (n + 15) / 16;
   const int q_splits = n_qt > kWarps ? 2 : 1;
   conformer_attn_mma_kernel<NT><<<B * heads * q_splits, kWarps * 32, smem, s>>>(qkv, rel, out, n, heads, dh,

@@ -314,7 +314,7 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
     if (NS == 3) RTDF_TRY(make_tmap_bf16(&mWl, a.w_lo, 2, dims, strides, box, sw));
     else mWl = mWh;
   }
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KW, CO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&conv_tc_kernel<KW, CO, NS>), (size_t)smem));
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   RTDF_CHECK_CUDA(launch_pdl(conv_tc_kernel<KW, CO, NS>, dim3(grid), dim3(kThreads), smem, stream, mAh, mAl, mWh, mWl, p));
   RTDF_LAUNCH_CHECK();

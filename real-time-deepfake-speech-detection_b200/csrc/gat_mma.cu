@@ -214,7 +214,7 @@ int launch(cudaStream_t s, const GraphView& x, int B, int n1, const GatRowWeight
   constexpr int KS = D / 16, NT = DO / 8;
   const size_t smem = (size_t)2 * NT * KS * 32 * sizeof(uint2) + (size_t)4 * DO * sizeof(float) +
                       (size_t)kWarps * (kMaxN + 2 * D) * sizeof(float) + (size_t)x.n * (D + 8) * sizeof(float);
-  RTDF_CHECK_CUDA(cudaFuncSetAttribute(gat_rows_mma_kernel<D, DO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&gat_rows_mma_kernel<D, DO>), (size_t)smem));
   const bool has_master = master_in != nullptr;
   const int n_iblocks = ceil_div(x.n, kWarps);
   dim3 grid(n_iblocks + (has_master ? 1 : 0), B);

@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <map>
+#include <utility>
+
 namespace rtdf {
 
 static thread_local char g_err[1024] = "";
@@ -29,6 +32,18 @@ bool pdl_enabled() {
     forced = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
   }
   return forced >= 0 ? forced == 1 : g_pdl_auto == 1;
+}
+
+cudaError_t raise_max_dyn_smem(const void* func, size_t bytes) {
+  static std::map<std::pair<int, const void*>, size_t> cur;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  size_t& have = cur[std::make_pair(dev, func)];
+  if (bytes <= have) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 
 static long long g_launches = 0;

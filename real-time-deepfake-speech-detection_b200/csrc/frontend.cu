@@ -108,7 +108,7 @@ template <typename TOut, bool kTanhGelu = false>
 __global__ void __launch_bounds__(256, 2)
 conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
-             float eps, TOut* __restrict__ out) {
+             float eps, TOut* __restrict__ out, int frames_per_cta) {
   __shared__ __align__(16) float sw[13][512];  // 10 taps | bias | gamma | beta
   for (int i = threadIdx.x; i < 10 * 512; i += 256) sw[0][i] = w_t[i];
   for (int i = threadIdx.x; i < 512; i += 256) {
@@ -121,8 +121,8 @@ conv0_kernel(const float* __restrict__ wav, int N, int L1, const float* __restri
   const int b = blockIdx.y;
   const float* xb = wav + (long long)b * N;
   // lane owns channels {j*128 + lane*4 + e}: 16 channels as 8 packed pairs
-  for (int g = warp; g < kConv0FramesPerCta / 4; g += 8) {
-    const int t0 = blockIdx.x * kConv0FramesPerCta + g * 4;
+  for (int g = warp; g < frames_per_cta / 4; g += 8) {
+    const int t0 = blockIdx.x * frames_per_cta + g * 4;
     if (t0 >= L1) break;
     // 4 frames need samples [5*t0, 5*t0 + 25)
     float xv = 0.f;
@@ -199,13 +199,15 @@ int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
   RTDF_REQUIRE(wav && w_t && gamma && beta && N >= 10 && B > 0 && B <= 65535, "conv0: bad arguments");
   RTDF_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "conv0: exactly one output must be given");
   const int L1 = (N - 10) / 5 + 1;
-  dim3 grid(ceil_div(L1, kConv0FramesPerCta), B);
+  // streaming chunks: 32 frames per CTA put the few thousand frames on ~100 SMs instead of ~13
+  const int fpc = (long long)B * L1 >= 2LL * kNumSMs * kConv0FramesPerCta ? kConv0FramesPerCta : 32;
+  dim3 grid(ceil_div(L1, fpc), B);
   if (out_f32)
-    conv0_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_f32);
+    conv0_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_f32, fpc);
   else if (tc_get_gelu_variant() == ACT_GELU_TANH)
-    conv0_kernel<bf16, true><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16);
+    conv0_kernel<bf16, true><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16, fpc);
   else
-    conv0_kernel<bf16><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16);
+    conv0_kernel<bf16><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, gamma, beta, eps, out_bf16, fpc);
   RTDF_LAUNCH_CHECK();
   return RTDF_OK;
 }

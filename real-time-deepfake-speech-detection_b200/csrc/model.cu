@@ -452,6 +452,7 @@ static int make_dims(int B, int N, Dims* d) {
 
 constexpr long long kSkinnyRows = 512;   // B*T up to which GEMMs are treated as weight-streaming problems
 constexpr long long kPdlRows = 1024;     // B*T up to which programmatic dependent launch is switched on
+constexpr long long kSmallConvRows = 16384;   // conv layers with at most this many output rows run as 64-wide GEMM + LN
 
 struct FrontWs {
   float* wav_pe;           // pre-emphasised copy
@@ -466,6 +467,8 @@ struct FrontWs {
   float* feats;            // (M,1024) fp32
   int* ln_cnt;             // per 128-row block tile counters of the fused GEMM + LayerNorm (zeroed each forward)
   float* partials;         // [<= 8][M][1024] K-split partial sums of out_proj / fc2 (streaming-chunk regime only)
+  float* conv_f32;         // (rows, 512) pre-LayerNorm conv output of the short conv layers (streaming-chunk regime only)
+  long long conv_f32_rows; // its capacity in rows (0 = not planned)
 };
 
 static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_feats, Bump& b, FrontWs* w) {
@@ -483,6 +486,8 @@ static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_
   w->feats = own_feats ? b.take<float>((long long)d.M * 1024) : nullptr;
   w->ln_cnt = b.take<int>(d.M / 128 + 2);
   w->partials = d.M <= kSkinnyRows ? b.take<float>(8LL * d.M * 1024) : nullptr;
+  w->conv_f32_rows = d.M <= kSkinnyRows && (long long)d.B * d.L[1] <= kSmallConvRows ? (long long)d.B * d.L[1] : 0;
+  w->conv_f32 = w->conv_f32_rows > 0 ? b.take<float>(w->conv_f32_rows * 512) : nullptr;
 }
 
 struct AasistWs {
@@ -646,7 +651,24 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   for (int i = 1; i < 7; ++i) {
     const FeConv& f = c->fe[i];
     const int Lin_ = d.L[i - 1], Lout = d.L[i];
-    if (bf) {
+    if (bf && w.conv_f32 && (long long)B * Lout <= w.conv_f32_rows && skinny_enabled()) {
+      // Streaming chunks: a full-row (N = 512) tile leaves one CTA per 128 output rows, each streaming the whole weight
+      // matrix.  64-wide tiles give 8x the CTAs; bias goes in the GEMM, LayerNorm + GELU in a row kernel (fp32 in between).
+      TcOperandA a;
+      a.ptr = static_cast<const bf16*>(cur);
+      a.k_extent = (long long)f.k * 512;
+      a.rows_per_batch = Lout;
+      a.batches = B;
+      a.row_stride = (long long)f.stride * 512;
+      a.batch_stride = (long long)Lin_ * 512;
+      TcEpilogue e;
+      e.bias = f.lin.b;
+      e.out_f32 = w.conv_f32;
+      e.ld_f32 = 512;
+      RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, 64, e));
+      RTDF_TRY(layernorm_rows_f32(s, w.conv_f32, (long long)B * Lout, 512, f.ln.g, f.ln.b, 1e-5f, ACT_GELU, nullptr,
+                                  static_cast<bf16*>(nxt)));
+    } else if (bf) {
       TcOperandA a;
       a.ptr = static_cast<const bf16*>(cur);
       a.k_extent = (long long)f.k * 512;

@@ -161,3 +161,28 @@ def test_forward_hooks_fire_with_fairseq_shaped_io():
     assert inp[0].shape == (T, B, 1024) and torch.equal(inp[0], layers[1].transpose(0, 1))
     assert torch.equal(out[0], layers[2].transpose(0, 1)) and out[1] == (None, None)
     assert seen["ssl"][0][0] is x and seen["ssl"][1] is feats
+
+
+def test_new_host_modules_have_no_cpu_path():
+    """staging / metrics / scoring pipeline refuse CPU devices and CPU tensors (the product path never falls back)."""
+    staging, metrics, scoring = pkg("staging"), pkg("metrics"), pkg("scoring")
+    with pytest.raises(RuntimeError):
+        staging.UtteranceStager(4000, 4, "cpu")
+    with pytest.raises(RuntimeError):
+        metrics.ScoreSink(8, "cpu")
+    with pytest.raises(RuntimeError):
+        metrics.roc_counts(torch.zeros(4), torch.zeros(4, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        staging.fit_duration(torch.zeros(10), torch.tensor([0, 10]), 4)
+    with pytest.raises(RuntimeError):
+        scoring.ScoringPipeline(object(), 8, 4, 16000, "cpu")
+
+
+def test_score_file_format_matches_reference_lines(tmp_path):
+    from oracle import eval_io_ref as E
+    scoring = pkg("scoring")
+    ids = ["LA_E_1000147", "LA_E_1000273", "DF_E_2000011"]
+    scores = torch.tensor([1.5, -0.25, 3.0e-5])
+    path = tmp_path / "scores.txt"
+    scoring.write_score_file(str(path), ids, scores)
+    assert path.read_text().splitlines(keepends=True) == E.score_lines(ids, scores.tolist())

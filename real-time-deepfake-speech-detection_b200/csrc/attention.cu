@@ -1,5 +1,7 @@
 // Fused attention tiles for the XLS-R transformer layers.
 #include "attention.cuh"
+
+#include <stdlib.h>
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -182,6 +184,9 @@ constexpr int kWsMaxStages = 6;
 
 struct AttWsParams {
   int T, H, Tk, n_qt, total_items, n_stages, stage_bytes, kv_bytes;
+  // RTDF_ATTN_DEBUG bit mask -- timing experiments only, the output is wrong when any bit is set (tools/attention_experiment.py):
+  // 1 = no row-max pass, 2 = exp pass on the first chunk only, 4 = no TMA loads, 8 = no S MMAs, 16 = no PV MMAs, 32 = no O store
+  int debug;
 };
 
 __global__ void __launch_bounds__(kWsThreads, 1)
@@ -211,9 +216,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(sfull_bar(g), 1);
-      mbar_init(pfull_bar(g), 128);
-      mbar_init(ofull_bar(g), 1);
-      mbar_init(tempty_bar(g), 128);
+      mbar_init(pfull_bar(g), 4);       // one elected arrive per softmax warp (128 per-thread arrives on one
+      mbar_init(ofull_bar(g), 1);       // shared-memory word serialise: ~1 us of the 16 us the empty pipeline costs)
+      mbar_init(tempty_bar(g), 4);
     }
     fence_mbar_init();
   }
@@ -238,6 +243,10 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
+        if (p.debug & 4) {
+          mbar_arrive(full_bar(s));
+          continue;
+        }
         mbar_expect_tx(full_bar(s), 16384u + 2u * p.kv_bytes);
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384, sV = sK + p.kv_bytes;
         tma_load_3d(sQ, &mapQ, full_bar(s), h * 64, qt * 128, b);
@@ -257,7 +266,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tc_fence_after();
         const uint32_t sV = base + s * p.stage_bytes + 16384 + p.kv_bytes;
         const uint32_t tP = tmem + g * 256, tO = tmem + g * 256 + 128;
-        for (int ks = 0; ks < ksteps; ++ks)
+        for (int ks = 0; ks < ksteps && !(p.debug & 16); ++ks)
           mma_bf16_ts(tO, tP + ks * 8, umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
         mma_commit(empty_bar(s));     // Q, K, V of this stage are no longer read
         mma_commit(ofull_bar(g));
@@ -270,7 +279,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma_bf16_ss(tmem + g * 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+          if (!(p.debug & 8))
+            mma_bf16_ss(tmem + g * 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
         mma_commit(sfull_bar(g));
         if (i > 0) issue_pv(i - 1);
       }
@@ -315,8 +325,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
               if (c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
         };
-        tmem_ld32(t_row, va);
-        for (int c = 0; c < nch; c += 2) {
+        if (!(p.debug & 1)) tmem_ld32(t_row, va);
+        for (int c = 0; c < nch && !(p.debug & 1); c += 2) {
           tmem_ld_wait_regs(va);
           if (c + 1 < nch) tmem_ld32(t_row + (c + 1) * 32, vb);
           chunk_max(va, c);
@@ -349,7 +359,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           tmem_st8(t_row + c * 16, pk);
           tmem_st8(t_row + c * 16 + 8, pk + 8);
         };
-        for (int c = 0; c < nch; c += 2) {
+        for (int c = 0; c < ((p.debug & 2) ? 1 : nch); c += 2) {
           tmem_ld_wait_regs(va);
           if (c + 1 < nch) tmem_ld32(t_row + (c + 1) * 32, vb);
           chunk_exp(va, c);
@@ -362,11 +372,12 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(pfull_bar(g));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar(g));
       mbar_wait(ofull_bar(g), ph);
       __syncwarp();
       tc_fence_after();
-      if (warp_active) {
+      if (warp_active && !(p.debug & 32)) {
         const float inv = 1.0f / sum;
         const int tq = qt * 128 + r;
         uint32_t v0[32], v1[32];
@@ -392,7 +403,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(g));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(g));
     }
   }
   tc_fence_before();
@@ -407,6 +419,14 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   RTDF_REQUIRE(qkv && ctx && B > 0 && H > 0, "attention_ws: bad arguments");
   RTDF_REQUIRE(T >= 1 && T <= 256, "attention_ws: T = %d frames unsupported (1..256; <= 5.1 s of audio)", T);
   AttWsParams p;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("RTDF_ATTN_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.T = T;
   p.H = H;
   p.Tk = (T + 15) & ~15;

@@ -98,7 +98,7 @@ def test_eval_loss_accuracy_oracle_self_consistency():
 
 
 def test_state_dict_wrapper_and_prefixed_checkpoints_load():
-    utils = pkg("utils")
+    utils = pkg("rtdf_utils")
     xa = pkg("models.xlsr_aasist")
     from oracle import eval_io_ref as E
     sd = {"module.a.weight": 1, "b.bias": 2}

@@ -8,14 +8,22 @@ per GPU).  A step = one pass of the scoring hot path over one batch of synthetic
 
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value     whole-job utt/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the model class's forward with pinned HOST input (H2D + D2H inside)
-  roofline  dominant kernel (tcgen05 GEMM, 128x256 tile): algorithmic FLOPs / CUDA-event time, vs the
+  e2e       same metric through scoring.ScoringPipeline with pinned HOST input (H2D + D2H inside)
+  parity    max |dlogit| of two rows of the timed batch against the CPU oracle (computed outside the timed region)
+  sweep     BASELINE.json configs[3] in small: a fixed set of 8,229 utterances seeded by GLOBAL index, sharded over
+            the ranks through scoring.score_utterances (ragged tail, one all-gather); sha256 of the gathered fp32
+            score vector -- identical at N = 1/2/4/8
+  latency   BASELINE.json configs[4]: p50 / p99 ms of single streaming-chunk calls (pinned host waveform -> host
+            score), XLSR-AASIST 1 s and 4 s, Conformer 1 s, batch 1 (N = 1 only)
+  roofline  dominant kernel (tcgen05 GEMM, 256-wide tiles): algorithmic FLOPs / CUDA-event time, vs the
             measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference forward timed on this box's host cores (bounded sample)
---impl reference times that oracle port (fp32 PyTorch on the host CPU) on the same metric/config.
+  cpu_baseline  the reference forward timed on this box's host cores (bounded sample)
+--impl reference times the reference's own model files (oracle/_ref archive, kind "reference"; the oracle port when
+the archive is absent, kind "port") in fp32 PyTorch on the host CPU, same metric / workload.
 """
 import argparse
 import ctypes
+import hashlib
 import importlib
 import json
 import os
@@ -33,17 +41,25 @@ N_SAMPLES = 64000          # 4 s @ 16 kHz (reference config.py:73-75)
 BATCH_PER_GPU = 64         # BASELINE.json configs[2]
 METRIC = "utterances/sec (4 s @16 kHz) XLSR-AASIST scoring"
 GFLOP_PER_UTT = 148.66
+WEIGHT_BYTES_BF16 = 631e6  # bf16 weights streamed once per forward (batch-1 HBM floor)
+SWEEP_UTTERANCES = 8192 + 37
+SWEEP_SEED = 7_000_000
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sweep-utterances", type=int, default=SWEEP_UTTERANCES)
+    ap.add_argument("--latency-calls", type=int, default=1000)
     return ap.parse_args()
 
 
@@ -109,15 +125,40 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference forward on the host cores
+# CPU arm: the reference's own model files (oracle/_ref archive) or, without them, the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_forward_timing(n_timed, n_warm, batch, layers):
+def build_cpu_reference(layers):
+    """(model, kind): the reference's XLSR_AASIST / My_XLSR_AASIST class from its own files when the archive made by
+    oracle/build_ref.py (or /root/reference itself) is available -- kind "reference" -- else the oracle port."""
+    import contextlib
+    import io
+
+    import torch
+    from oracle import build_ref
+    from oracle.aasist_ref import perturb_norm_stats
+    kw = {} if layers == 24 else {"num_layers": layers, "order": "first"}
+    name = "XLSR_AASIST" if layers == 24 else "My_XLSR_AASIST"
+    mods = None
+    try:
+        mods = build_ref.import_reference_models()
+    except Exception as e:  # noqa: BLE001
+        print(f"bench: reference files not importable ({e!r}); timing the oracle port", file=sys.stderr)
+    if mods is not None:
+        torch.manual_seed(1024)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = getattr(mods[0], name)("cpu", None, **kw).eval()
+        perturb_norm_stats(model, seed=1025)
+        return model, "reference"
+    from oracle import models_ref as O
+    return O.build(name, seed=1024, **kw), "port"
+
+
+def cpu_forward_timing(n_timed, n_warm, batch, layers, also_batch=None):
     import torch
     from oracle import models_ref as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model = O.build("XLSR_AASIST" if layers == 24 else "My_XLSR_AASIST", seed=1024,
-                    **({} if layers == 24 else {"num_layers": layers, "order": "first"}))
+    model, kind = build_cpu_reference(layers)
     x = O.synth_waveforms(batch, N_SAMPLES, seed=2021)
     with torch.no_grad():
         for _ in range(n_warm):
@@ -127,28 +168,38 @@ def cpu_forward_timing(n_timed, n_warm, batch, layers):
             t0 = time.perf_counter()
             model(x)
             times.append(time.perf_counter() - t0)
+        other = None
+        if also_batch:
+            xb = O.synth_waveforms(also_batch, N_SAMPLES, seed=2021)
+            t0 = time.perf_counter()
+            model(xb)
+            dt = time.perf_counter() - t0
+            other = {"batch": also_batch, "value": also_batch / dt, "unit": "utt/s", "ms_per_step": 1e3 * dt,
+                     "note": "one forward at the B200 arm's batch, no warm-up"}
     total = sum(times)
-    return {"utt_per_s": batch * n_timed / total, "ms_per_step": 1e3 * total / n_timed, "cores": cores,
-            "best_utt_per_s": batch / min(times)}
+    return {"utt_per_s": batch * n_timed / total, "ms_per_step": 1e3 * total / n_timed, "cores": cores, "kind": kind,
+            "best_utt_per_s": batch / min(times), "other": other}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU forward (oracle port; the reference's own files need fairseq and
-    cannot travel to the GPU box) on all host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU forward (its own model files over fairseq / conformer shims when the
+    oracle/_ref archive is present, else the oracle port) on all host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    batch = 4
-    steps = max(1, args.steps)
-    r = cpu_forward_timing(steps, max(1, min(args.warmup, 2)), batch, args.layers)
-    sample = f"{steps} timed forwards of {batch} utterances (4 s @16 kHz), fp32, torch.set_num_threads({r['cores']})"
+    batch = 4                                   # the batch the host CPU does best at (B = 1, 4, 8 probed in round 1)
+    steps = max(1, min(args.steps, 8))          # bounded sample: a step is ~0.4 s of 16-core work
+    r = cpu_forward_timing(steps, max(1, min(args.warmup, 2)), batch, args.layers, also_batch=args.batch)
+    sample = (f"{steps} timed forwards of {batch} utterances (4 s @16 kHz), fp32, torch.set_num_threads({r['cores']}); "
+              f"{'reference model files (oracle/_ref)' if r['kind'] == 'reference' else 'oracle port'}")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["utt_per_s"], "unit": "utt/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "XLSR-AASIST (XLS-R 300M 24x1024 + AASIST), random init, 4 s utterances, host CPU",
                    "batch": batch, "n_samples": N_SAMPLES, "layers": args.layers},
-        "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["utt_per_s"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "same_batch_as_b200_arm": r["other"],
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -163,6 +214,65 @@ def synth_on_device(torch, batch, n, seed, device):
     t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
     x = 0.1 * torch.randn(batch, n, generator=g, device=device) + 0.05 * torch.sin(2 * torch.pi * 220.0 * t)
     return x.clamp_(-1, 1).contiguous()
+
+
+def sweep_utterances_to_host(torch, lo, hi, n, device):
+    """Utterances [lo, hi) of the fixed sweep set, each a function of its GLOBAL index only (Philox stream seeded with
+    SWEEP_SEED + index), generated on the device and parked in pinned host memory (the DataLoader's role)."""
+    pool = torch.empty(max(hi - lo, 1), n, dtype=torch.float32).pin_memory()
+    g = torch.Generator(device=device)
+    t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
+    tone = 0.05 * torch.sin(2 * torch.pi * 220.0 * t)
+    chunk = 256
+    for c0 in range(lo, hi, chunk):
+        c1 = min(c0 + chunk, hi)
+        buf = torch.empty(c1 - c0, n, dtype=torch.float32, device=device)
+        for i in range(c0, c1):
+            g.manual_seed(SWEEP_SEED + i)
+            buf[i - c0] = torch.randn(n, generator=g, device=device)
+        buf.mul_(0.1).add_(tone).clamp_(-1, 1)
+        pool[c0 - lo:c1 - lo].copy_(buf)
+    torch.cuda.synchronize()
+    return pool
+
+
+def percentile(sorted_vals, q):
+    if not sorted_vals:
+        return None
+    k = min(len(sorted_vals) - 1, max(0, int(round(q * (len(sorted_vals) - 1)))))
+    return sorted_vals[k]
+
+
+def latency_config(torch, model, n_samples, batch, device, n_warm, n_calls, hbm_gbs, weight_bytes):
+    """One streaming configuration: per call, pinned host waveform -> device, forward, score -> pinned host, sync.
+    Wall-clock per call (what a streaming client sees) and CUDA-event time of the device part."""
+    eng = model.engine()
+    host_in = (0.1 * torch.randn(batch, n_samples)).pin_memory()
+    host_out = torch.empty(batch, dtype=torch.float32).pin_memory()
+    dev_in = torch.empty(batch, n_samples, dtype=torch.float32, device=device)
+    stream = torch.cuda.current_stream(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall, devt = [], []
+    for i in range(n_warm + n_calls):
+        t0 = time.perf_counter()
+        e0.record(stream)
+        dev_in.copy_(host_in, non_blocking=True)
+        logits = eng.forward(dev_in)
+        host_out.copy_(logits[:, 1], non_blocking=True)
+        e1.record(stream)
+        e1.synchronize()
+        t1 = time.perf_counter()
+        if i >= n_warm:
+            wall.append(1e3 * (t1 - t0))
+            devt.append(e0.elapsed_time(e1))
+    wall.sort(); devt.sort()
+    floor_ms = 1e3 * weight_bytes / (hbm_gbs * 1e9)
+    p50 = percentile(wall, 0.50)
+    return {"batch": batch, "n_samples": n_samples, "frames": eng.num_frames(n_samples), "calls": n_calls, "warm": n_warm,
+            "p50_ms": p50, "p99_ms": percentile(wall, 0.99), "mean_ms": sum(wall) / len(wall),
+            "device_p50_ms": percentile(devt, 0.50), "device_p99_ms": percentile(devt, 0.99),
+            "hbm_floor_ms": floor_ms, "hbm_floor_frac": floor_ms / p50,
+            "timing": "host wall clock per call: pinned H2D + forward (CUDA-graph replay) + D2H of the score + sync"}
 
 
 def run_b200(args):
@@ -187,7 +297,7 @@ def run_b200(args):
     scoring = importlib.import_module(PKG + ".scoring")
     lib = native.load()
 
-    torch.manual_seed(1024)
+    torch.manual_seed(1024)                       # identical weights on every rank and at every N (sweep digest)
     if args.layers == 24:
         model = xa.XLSR_AASIST("cpu", None)
     else:
@@ -207,6 +317,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     # kernels per forward, counted on one eager (non-graph) forward: the timed steps replay a CUDA graph of them
     graph_on = eng.use_graph
     eng.use_graph = False
@@ -216,8 +333,17 @@ def run_b200(args):
     eng.use_graph = graph_on
 
     # ---- device-resident throughput ("value") --------------------------------------------------
+    # W warm-up steps, then ~1 s more of the same steps so the clocks sit where a long scoring job holds them (power cap)
     for i in range(W):
         eng.forward(inputs[i % n_bufs])
+    torch.cuda.synchronize()
+    extra_warm = 0
+    t_w = time.time()
+    while time.time() - t_w < 1.0:
+        for i in range(8):
+            eng.forward(inputs[i % n_bufs])
+        torch.cuda.synchronize()
+        extra_warm += 8
     if world > 1:
         scoring.gather_scores(scores[:B], world * B, B)
     barrier()
@@ -239,15 +365,12 @@ def run_b200(args):
     ev1.record()
     barrier()
     t_wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = launches_per_forward * K
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * K * B / (ms / 1e3)
     assert bool(torch.isfinite(all_scores).all()), "non-finite scores"
+    timed_logits_first = eng.forward(inputs[0]).clone()       # same graph replay as timed step 0 (deterministic)
 
     # ---- end-to-end through the package's scoring API (pinned HOST input -> HOST scores) -----------
     # Every step: H2D of that step's batch from pinned host memory (side stream), forward, D2H of its scores.
@@ -265,12 +388,8 @@ def run_b200(args):
     host_scores = pipe.finish()
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     assert bool(torch.isfinite(host_scores).all()) and host_scores.numel() == (Ke + 2) * B
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
     e2e_value = world * Ke * B / (ms_e2e / 1e3)
     # the reference's own loop shape, unpipelined (blocking .cpu() per batch), for comparison
     dev_in = torch.empty(B, N, dtype=torch.float32, device=device)
@@ -286,6 +405,34 @@ def run_b200(args):
     s1.record()
     barrier()
     serial_value = Ks * B / (s0.elapsed_time(s1) / 1e3)
+    del pipe, host
+
+    # ---- sweep: BASELINE.json configs[3] in small (fixed utterance set, sharded, ragged tail, one gather) ----------
+    sweep = None
+    if not args.no_sweep:
+        n_items = int(args.sweep_utterances)
+        lo, hi, per = scoring.shard_range(n_items, rank, world)
+        pool = sweep_utterances_to_host(torch, lo, hi, N, device)     # untimed: the dataset, resident in pinned memory
+
+        def load_batch(b_lo, b_hi, out):
+            return pool[b_lo - lo:b_hi - lo]                         # zero-copy: the pinned slice goes straight to H2D
+
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        gathered = scoring.score_utterances(model, n_items, load_batch, N, B, device, rank=rank, world=world)
+        w1.record()
+        barrier()
+        ms_sweep = max_over_ranks(w0.elapsed_time(w1))
+        vec = gathered.detach().cpu().contiguous()
+        assert vec.numel() == n_items and bool(torch.isfinite(vec).all()), "sweep: missing or non-finite scores"
+        sweep = {"utterances": n_items, "utt_per_s": n_items / (ms_sweep / 1e3), "ms": ms_sweep,
+                 "sha256": hashlib.sha256(vec.numpy().tobytes()).hexdigest(),
+                 "per_rank": per, "batch": B, "ragged_tail": (hi - lo) % B if rank == 0 else None,
+                 "score_head": [float(v) for v in vec[:3]],
+                 "api": "scoring.score_utterances (ScoringPipeline per rank, throughput regime, one all_gather_into_tensor); "
+                        "utterance i = f(SWEEP_SEED + i) only, so the digest must be equal at N = 1/2/4/8"}
+        del pool
 
     # ---- roofline leg: CUDA-event time of every launch of the dominant kernel inside real steps ---
     roofline = None
@@ -299,28 +446,68 @@ def run_b200(args):
         pms, pfl, pn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
         native.check(lib.rtdf_profile_end(256, ctypes.byref(pms), ctypes.byref(pfl), ctypes.byref(pn)), "rtdf_profile_end")
         peaks = measured_peaks()
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # from the committed ncu --set full capture
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+        traffic, traffic_src = None, None
+        for name in ("r02_traffic.json", "r01_traffic.json"):         # from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get("dram_bytes_per_launch")
+                traffic_src = f"DRAM bytes per launch (ncu, profiles/{name})"
+                break
         if pn.value > 0 and pms.value > 0:
             achieved = pfl.value / (pms.value * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM, 256-wide tiles: tc_gemm_2sm_kernel (CTA pair) / tc_gemm_kernel<256,64> (QKV/out/FFN projections)",
                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                            "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)",
+                        "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
+                        "traffic": traffic, "traffic_unit": traffic_src,
                         "launches_timed": pn.value, "avg_launch_ms": pms.value / pn.value,
                         "flops_per_launch_avg": pfl.value / pn.value, "peak_source": peaks["source"] + ", sustained",
+                        "share_of_step": (pms.value / 2) / (ms / K),
                         "whole_path_frac": value * GFLOP_PER_UTT * 1e9 / world / 1e12 / peaks["bf16_sustained"]}
+
+    # ---- parity of the timed batch against the CPU oracle (rank 0, outside every timed region) -------------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import models_ref as O
+        kw = {} if args.layers == 24 else {"num_layers": args.layers, "order": "first"}
+        ora = O.build("XLSR_AASIST" if args.layers == 24 else "My_XLSR_AASIST", seed=1, perturb=False, **kw)
+        ora.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+        rows = [0, B - 1] if B > 1 else [0]
+        with torch.no_grad():
+            ref = ora(inputs[0][rows].cpu())
+        got = timed_logits_first[rows].cpu()
+        parity = {"rows": rows, "max_abs_dlogit": float((got - ref).abs().max()), "tolerance": 1e-3,
+                  "oracle_logits_row0": [float(v) for v in ref[0]], "b200_logits_row0": [float(v) for v in got[0]],
+                  "note": "timed batch (inputs[0]) through the same CUDA-graph replay as the timed steps vs the fp32 CPU "
+                          "oracle with the product model's weights; north_star bound 1e-2, asserted bound 1e-3"}
+        parity["ok"] = parity["max_abs_dlogit"] <= parity["tolerance"]
+        del ora
+
+    # ---- streaming latency (rank 0, N = 1 only): BASELINE.json configs[4] -------------------------------------
+    latency = None
+    if rank == 0 and world == 1 and not args.no_latency and args.layers == 24:
+        peaks = measured_peaks()
+        n_warm, n_calls = 200, max(100, args.latency_calls)
+        latency = {}
+        latency["xlsr_aasist_b1_1s"] = latency_config(torch, model, 16000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], WEIGHT_BYTES_BF16)
+        latency["xlsr_aasist_b1_4s"] = latency_config(torch, model, 64000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], WEIGHT_BYTES_BF16)
+        cb = importlib.import_module(PKG + ".models.conformer_baseline")
+        torch.manual_seed(1024)
+        conf = cb.Model("cpu", None).to(device).eval()
+        conf.rtdf_precision = "bf16"
+        conf.engine()
+        conf.rtdf_frozen = True
+        latency["conformer_b1_1s"] = latency_config(torch, conf, 16000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], 636e6)
+        del conf
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_forward_timing(3, 1, 4, args.layers)
-        cpu = {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": "port",
-               "sample": "3 timed forwards of 4 utterances (4 s @16 kHz) after 1 warm-up, fp32 oracle, "
-                         f"torch.set_num_threads({r['cores']})"}
+        cpu = {"value": r["utt_per_s"], "unit": "utt/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": "3 timed forwards of 4 utterances (4 s @16 kHz) after 1 warm-up, fp32, "
+                         f"torch.set_num_threads({r['cores']}); "
+                         f"{'reference model files (oracle/_ref)' if r['kind'] == 'reference' else 'oracle port'}"}
 
     if rank == 0:
         T = eng.num_frames(N)
@@ -333,6 +520,7 @@ def run_b200(args):
                        "global_batch": world * B, "batch_per_gpu": B, "n_samples": N, "frames": T, "layers": args.layers,
                        "parallelism": f"dp{world} (independent shards, one all-gather of scores)",
                        "cuda_graph": bool(graph_on), "kernels_per_forward": int(launches_per_forward),
+                       "extra_warm_steps": extra_warm,
                        "l2": "per-step working set (631 MB bf16 weights + >1.5 GB activations) exceeds the 126 MB L2; "
                              "inputs rotate over 4 device buffers"},
             "clocks": clocks,
@@ -343,6 +531,9 @@ def run_b200(args):
                     "serial_loop_value": serial_value,
                     "serial_loop_api": "model(batch_x)[:, 1].cpu() per batch, blocking (rank 0)"},
             "gpu_launches": int(launches),
+            "parity": parity,
+            "sweep": sweep,
+            "latency": latency,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "gflop_per_utt": GFLOP_PER_UTT,

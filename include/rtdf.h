@@ -57,6 +57,14 @@ typedef struct rtdf_model_desc {
   int gat_impl;       /* bf16 mode, graph-attention rows: 0 = tensor cores (mma.sync, (hi,lo) bf16 pairs), 1 = fp32 SIMT */
 } rtdf_model_desc;
 
+/* Kernel-selection regime of the forward calls.  AUTO: batches of at most 512 frames in flight (streaming chunks,
+ * batch 1-8 x 1 s) use the weight-streaming tiles (64-wide, deterministic split-K) -- lowest latency, but in bf16 an
+ * utterance's logits then depend at rounding level on how many utterances share its batch.  THROUGHPUT: always the
+ * large-batch tiles; per-utterance results are independent of batch composition (bit-identical), which is what the
+ * sharded scoring sweep (ragged last batch, 1/2/4/8 GPUs) relies on.  The reference has no counterpart (cuBLAS picks
+ * kernels by shape too); fp32 mode is batch-invariant in both regimes. */
+enum rtdf_regime { RTDF_REGIME_AUTO = 0, RTDF_REGIME_THROUGHPUT = 1 };
+
 /* Optional intermediate outputs of a forward call (device pointers, may be NULL). */
 typedef struct rtdf_taps {
   float* feats;    /* (B, T, 1024) XLS-R output features (fe.py:17-21 'x')          */
@@ -77,6 +85,8 @@ int rtdf_load_weight(rtdf_ctx* ctx, const char* key, const void* data, const int
 /* Packs weights: bf16 casts, fused QKV (1/8 folded into W_q, b_q), weight-norm fold of pos_conv,
  * eval-BatchNorm folds, implicit-GEMM conv weight layout.  Fails listing the first missing key. */
 int rtdf_finalize(rtdf_ctx* ctx);
+/* Selects the rtdf_regime used by subsequent forward calls on this context (default RTDF_REGIME_AUTO). */
+int rtdf_set_regime(rtdf_ctx* ctx, int regime);
 void rtdf_destroy(rtdf_ctx* ctx);
 const char* rtdf_last_error(void);
 
@@ -161,6 +171,21 @@ int rtdf_gat_rows(int d, int dout, const float* x, int batch, int n, int n1, con
 /* GraphPool (aasist_modules.py:306-338) on h (B,n,D): out (B,k,D), idx (B,k) descending score. */
 int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, const float* b, int k, float* out,
                     int32_t* idx, void* stream);
+
+/* Conformer block kernels.  The reference instantiates lucidrains' ConformerBlock(dim=144, dim_head=36, heads=4,
+ * ff_mult=4, conv_expansion_factor=2, conv_kernel_size=31) at models/conformer_baseline.py:16-18; these two entry
+ * points are its two non-GEMM stages.
+ * Shaw relative-position multi-head self-attention: qkv (B*n, 3*heads*dh) = [q | k | v] (no bias), rel_pos [1025][dh]
+ * fp32 (Embedding, max_pos_emb 512): out (B*n, heads*dh) = softmax_j(dh^-1/2 (q_i.k_j + q_i.R[clamp(i-j,-512,512)+512])) v.
+ * is_bf16: 0 = fp32 SIMT kernel; 1 with impl 0 = tensor-core kernel (mma.sync; n <= 208, dh <= 40 even, else
+ * RTDF_STATUS_UNSUPPORTED), impl 1 = what the forward uses (tensor cores inside the envelope, bf16 SIMT outside). */
+int rtdf_conformer_attention(const void* qkv, const float* rel_pos, void* out, int batch, int n, int heads, int dh,
+                             int is_bf16, int impl, void* stream);
+/* Convolution module after the first pointwise conv: in (B*n, 2*inner) -> GLU over channels (first half * sigmoid(second
+ * half)) -> depth-wise Conv1d(inner, k, groups=inner, "same" padding (k/2, k/2 - (k+1)%2)) + bias -> eval BatchNorm1d
+ * folded to bn_s / bn_t -> Swish -> out (B*n, inner).  w: [inner][k] fp32. */
+int rtdf_conformer_glu_dwconv(const void* in, void* out, int batch, int n, int inner, int k, const float* w,
+                              const float* bias, const float* bn_s, const float* bn_t, int is_bf16, void* stream);
 
 /* Shifted-row tcgen05 convolution on zero-padded channels-last planes (bf16-mode AASIST residual encoder and
  * attention map; replaces the cuDNN convs behind models/aasist_modules.py:340-397, models/xlsr_aasist.py:103).

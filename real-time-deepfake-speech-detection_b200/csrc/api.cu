@@ -3,6 +3,7 @@
 #include "../../include/rtdf.h"
 #include "aasist.cuh"
 #include "attention.cuh"
+#include "conformer.cuh"
 #include "conv_tc.cuh"
 #include "frontend.cuh"
 #include "gemm_simt.cuh"
@@ -257,6 +258,29 @@ int rtdf_graph_pool(const float* h, int batch, int n, int d, const float* w, con
   g.n = n;
   g.batch_stride = (long long)n * d;
   return aasist_graph_pool(static_cast<cudaStream_t>(stream), d, g, batch, w, b, k, out, idx);
+}
+
+// ---- Conformer block kernels (lucidrains ConformerBlock instantiated at reference models/conformer_baseline.py:16-18) ----
+int rtdf_conformer_attention(const void* qkv, const float* rel_pos, void* out, int batch, int n, int heads, int dh,
+                             int is_bf16, int impl, void* stream) {
+  RTDF_REQUIRE(qkv && rel_pos && out, "rtdf_conformer_attention: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!is_bf16)
+    return conformer_attention_f32(s, static_cast<const float*>(qkv), rel_pos, static_cast<float*>(out), batch, n, heads, dh);
+  if (impl == 0)   // tensor-core kernel only: outside its envelope this reports RTDF_STATUS_UNSUPPORTED instead of falling back
+    return conformer_attention_mma(s, static_cast<const bf16*>(qkv), rel_pos, static_cast<bf16*>(out), batch, n, heads, dh);
+  return conformer_attention_bf16(s, static_cast<const bf16*>(qkv), rel_pos, static_cast<bf16*>(out), batch, n, heads, dh);
+}
+
+int rtdf_conformer_glu_dwconv(const void* in, void* out, int batch, int n, int inner, int k, const float* w,
+                              const float* bias, const float* bn_s, const float* bn_t, int is_bf16, void* stream) {
+  RTDF_REQUIRE(in && out && w && bias && bn_s && bn_t, "rtdf_conformer_glu_dwconv: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_bf16)
+    return conformer_glu_dwconv_bf16(s, static_cast<const bf16*>(in), static_cast<bf16*>(out), batch, n, inner, k, w, bias,
+                                     bn_s, bn_t);
+  return conformer_glu_dwconv_f32(s, static_cast<const float*>(in), static_cast<float*>(out), batch, n, inner, k, w, bias,
+                                  bn_s, bn_t);
 }
 
 }  // extern "C"

@@ -9,6 +9,9 @@
 // tcgen05.commit.  Replaces the cuBLAS/cuDNN calls behind fairseq's Linear / Conv1d layers
 // (reference models/fe.py:19).
 #include "gemm_tc.cuh"
+
+#include <atomic>
+#include <mutex>
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -41,16 +44,19 @@ struct TcKernelParams {
 
 // ---- optional per-launch timing (CUDA events on the launching stream), used by bench.py's roofline leg ----
 struct ProfRec { cudaEvent_t a, b; double flops; int variant; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
 static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;     // launches may come from several host threads (one context each)
 
 void tc_profile_begin() {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
   g_prof_on = true;
 }
 int tc_profile_end(int variant, double* ms_total, double* flops_total, int* launches) {
   g_prof_on = false;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
   double ms = 0, fl = 0;
   int n = 0;
   for (auto& r : g_prof) {
@@ -1336,6 +1342,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof.push_back(rec);
   }
   return RTDF_OK;
@@ -1396,6 +1403,7 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof.push_back(rec);
   }
   return RTDF_OK;
@@ -1448,6 +1456,7 @@ static int launch_conv_ln(cudaStream_t stream, const TcOperandA& A, const bf16* 
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof.push_back(rec);
   }
   return RTDF_OK;
@@ -1500,6 +1509,7 @@ static int launch_conv_ln_2sm(cudaStream_t stream, const TcOperandA& A, const bf
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof.push_back(rec);
   }
   return RTDF_OK;

@@ -3,6 +3,9 @@
 
 #include <stdlib.h>
 
+#include <iterator>
+#include <set>
+
 #include "attention.cuh"
 #include "conformer.cuh"
 #include "conv_tc.cuh"
@@ -48,6 +51,13 @@ static int get_ptr(rtdf_ctx* c, const std::string& key, const float** out, long 
   return RTDF_OK;
 }
 
+// bf16 mode keeps one packed bf16 copy of every GEMM-sized weight; its fp32 source (the state-dict copy made by
+// rtdf_load_weight, or an fp32 staging buffer of the packing) is released at the end of rtdf_finalize.
+constexpr long long kDropMinNumel = 32768;
+static void drop_after_finalize(rtdf_ctx* c, const void* p) {
+  if (c->d.precision == RTDF_PREC_BF16 && p) c->scratch.push_back(const_cast<void*>(p));
+}
+
 static int to_bf16(rtdf_ctx* c, const float* src, long long n, const bf16** out) {
   bf16* p;
   RTDF_TRY(dalloc(c, n, &p));
@@ -61,7 +71,13 @@ static int make_lin(rtdf_ctx* c, const std::string& prefix, int n, int k, bool b
   out->k = k;
   RTDF_TRY(get_ptr(c, prefix + ".weight", &out->w, (long long)n * k));
   if (bias) RTDF_TRY(get_ptr(c, prefix + ".bias", &out->b, n));
-  if (c->d.precision == RTDF_PREC_BF16) RTDF_TRY(to_bf16(c, out->w, (long long)n * k, &out->wb));
+  if (c->d.precision == RTDF_PREC_BF16) {
+    RTDF_TRY(to_bf16(c, out->w, (long long)n * k, &out->wb));
+    if ((long long)n * k >= kDropMinNumel) {   // small matrices (fc5, out_layer) are also read as fp32 by row kernels
+      drop_after_finalize(c, out->w);
+      out->w = nullptr;
+    }
+  }
   return RTDF_OK;
 }
 
@@ -138,7 +154,12 @@ static int pack_xlsr(rtdf_ctx* c) {
     f.lin.w = wp;
     f.lin.n = 512;
     f.lin.k = ci * f.k;
-    if (bf && i > 0) RTDF_TRY(to_bf16(c, wp, 512LL * ci * f.k, &f.lin.wb));
+    if (bf && i > 0) {
+      RTDF_TRY(to_bf16(c, wp, 512LL * ci * f.k, &f.lin.wb));
+      drop_after_finalize(c, wp);
+      drop_after_finalize(c, w);
+      f.lin.w = nullptr;
+    }
   }
   RTDF_TRY(make_ln(c, P + "layer_norm", 512, &c->fp_ln));
   RTDF_TRY(make_lin(c, P + "post_extract_proj", 1024, 512, true, &c->proj));
@@ -153,7 +174,12 @@ static int pack_xlsr(rtdf_ctx* c) {
     c->pos.w = wp;
     c->pos.n = 1024;
     c->pos.k = 8192;
-    if (bf) RTDF_TRY(to_bf16(c, wp, 1024LL * 8192, &c->pos.wb));
+    if (bf) {
+      RTDF_TRY(to_bf16(c, wp, 1024LL * 8192, &c->pos.wb));
+      drop_after_finalize(c, wp);
+      drop_after_finalize(c, v);
+      c->pos.w = nullptr;
+    }
   }
   c->layers.resize(c->d.n_layers);
   for (int l = 0; l < c->d.n_layers; ++l) {
@@ -170,6 +196,7 @@ static int pack_xlsr(rtdf_ctx* c) {
       RTDF_TRY(get_ptr(c, lp + ".self_attn." + names[j] + ".bias", &bj, 1024));
       RTDF_CHECK_CUDA(cudaMemcpy(w + j * 1024LL * 1024, wj, 1024LL * 1024 * 4, cudaMemcpyDeviceToDevice));
       RTDF_CHECK_CUDA(cudaMemcpy(b + j * 1024, bj, 1024 * 4, cudaMemcpyDeviceToDevice));
+      drop_after_finalize(c, wj);
     }
     RTDF_TRY(scale_rows_f32(0, w, 1024, 1024, 0.125f));
     RTDF_TRY(scale_rows_f32(0, b, 1, 1024, 0.125f));
@@ -177,7 +204,11 @@ static int pack_xlsr(rtdf_ctx* c) {
     L.qkv.b = b;
     L.qkv.n = 3072;
     L.qkv.k = 1024;
-    if (bf) RTDF_TRY(to_bf16(c, w, 3072LL * 1024, &L.qkv.wb));
+    if (bf) {
+      RTDF_TRY(to_bf16(c, w, 3072LL * 1024, &L.qkv.wb));
+      drop_after_finalize(c, w);
+      L.qkv.w = nullptr;
+    }
     RTDF_TRY(make_lin(c, lp + ".self_attn.out_proj", 1024, 1024, true, &L.out));
     RTDF_TRY(make_lin(c, lp + ".fc1", 4096, 1024, true, &L.fc1));
     RTDF_TRY(make_lin(c, lp + ".fc2", 1024, 4096, true, &L.fc2));
@@ -600,6 +631,13 @@ static bool skinny_enabled() {
   return v == 1;
 }
 
+// Streaming-chunk regime (64-wide weight-streaming tiles, split-K, GEMM + LayerNorm-row convs): chosen from the number
+// of rows in flight unless the caller pinned the throughput regime (rtdf_set_regime), in which case an utterance's
+// scores do not depend on the batch it travels in (ragged last batches, multi-GPU shards).
+static bool skinny_rows(const rtdf_ctx* c, long long rows) {
+  return c->regime != RTDF_REGIME_THROUGHPUT && rows <= kSkinnyRows && skinny_enabled();
+}
+
 static bool conv_2sm_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -623,7 +661,7 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
   if (c->d.precision == RTDF_PREC_BF16) {
     int variant = L.n >= 256 ? 256 : (L.n >= 128 ? 128 : 64);
     if (variant == 256 && L.n % 256 == 0 && rows >= 2048 && gemm_2sm_enabled()) variant = 2256;   // CTA-pair tiles
-    if (rows <= kSkinnyRows && L.n % 64 == 0 && skinny_enabled()) {
+    if (skinny_rows(c, rows) && L.n % 64 == 0) {
       // Streaming chunks (batch 1-8 x 49 frames, or one 4 s utterance): the GEMM is a weight-streaming problem, so
       // the tile count -- not the tile shape -- sets the time: 64-wide tiles give 4x the CTAs of the 256-wide ones
       // (the residual GEMMs of the transformer layers additionally split K, see run_frontend).
@@ -651,7 +689,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   for (int i = 1; i < 7; ++i) {
     const FeConv& f = c->fe[i];
     const int Lin_ = d.L[i - 1], Lout = d.L[i];
-    if (bf && w.conv_f32 && (long long)B * Lout <= w.conv_f32_rows && skinny_enabled()) {
+    if (bf && w.conv_f32 && (long long)B * Lout <= w.conv_f32_rows && skinny_rows(c, M)) {
       // Streaming chunks: a full-row (N = 512) tile leaves one CTA per 128 output rows, each streaming the whole weight
       // matrix.  64-wide tiles give 8x the CTAs; bias goes in the GEMM, LayerNorm + GELU in a row kernel (fp32 in between).
       TcOperandA a;
@@ -754,7 +792,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   const bool fuse_ln = bf && fuse_ln_enabled();   // opt-in: measured slower both at B=64 and for streaming chunks
   // Streaming chunks: out_proj / fc2 (16 output tiles per 128 rows, K up to 4096) split K over the idle SMs; the partial
   // sums land in w.partials and the LayerNorm that follows adds them to x in split order (deterministic).
-  const bool splitk = bf && !fuse_ln && !layer_taps && M <= kSkinnyRows && skinny_enabled() && w.partials;
+  const bool splitk = bf && !fuse_ln && !layer_taps && skinny_rows(c, M) && w.partials;
   const int sp_out = splitk ? tc_plan_splits(M, 1024, 1024) : 1, sp_fc2 = splitk ? tc_plan_splits(M, 1024, 4096) : 1;
   int pending = 0;      // K-split partials of the previous residual GEMM not yet folded into x
   auto layer_ln = [&](const Norm& n, float* of32, bf16* ob16) -> int {
@@ -1234,6 +1272,13 @@ int rtdf_load_weight(rtdf_ctx* c, const char* key, const void* data, const int64
   return RTDF_OK;
 }
 
+int rtdf_set_regime(rtdf_ctx* c, int regime) {
+  RTDF_REQUIRE(c, "rtdf_set_regime: null context");
+  RTDF_REQUIRE(regime == RTDF_REGIME_AUTO || regime == RTDF_REGIME_THROUGHPUT, "rtdf_set_regime: unknown regime %d", regime);
+  c->regime = regime;
+  return RTDF_OK;
+}
+
 int rtdf_finalize(rtdf_ctx* c) {
   RTDF_REQUIRE(c, "rtdf_finalize: null context");
   if (c->finalized) return RTDF_OK;
@@ -1242,6 +1287,18 @@ int rtdf_finalize(rtdf_ctx* c) {
   if (c->d.backend == RTDF_BACKEND_AASIST) RTDF_TRY(pack_aasist(c));
   if (c->d.backend == RTDF_BACKEND_CONFORMER) RTDF_TRY(pack_conformer(c));
   RTDF_CHECK_CUDA(cudaDeviceSynchronize());
+  if (!c->scratch.empty()) {   // bf16 mode: release the fp32 sources of the packed GEMM weights
+    std::set<void*> dead(c->scratch.begin(), c->scratch.end());
+    for (auto it = c->raw.begin(); it != c->raw.end();)
+      it = dead.count(it->second.p) ? c->raw.erase(it) : std::next(it);
+    std::vector<void*> keep;
+    for (void* p : c->owned) {
+      if (dead.count(p)) cudaFree(p);
+      else keep.push_back(p);
+    }
+    c->owned.swap(keep);
+    c->scratch.clear();
+  }
   c->finalized = true;
   return RTDF_OK;
 }

@@ -108,8 +108,10 @@ struct rtdf_ctx {
   int device = 0;
   rtdf_model_desc d{};
   bool finalized = false;
+  int regime = RTDF_REGIME_AUTO;   // rtdf_set_regime
   std::map<std::string, rtdf::Raw> raw;
   std::vector<void*> owned;
+  std::vector<void*> scratch;      // fp32 sources of packed bf16 weights, released at the end of rtdf_finalize
   // XLS-R
   rtdf::FeConv fe[7];
   rtdf::Norm fp_ln;

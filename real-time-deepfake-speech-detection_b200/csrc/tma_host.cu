@@ -4,7 +4,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <utility>
 
 namespace rtdf {
@@ -23,7 +25,9 @@ const char* get_error() { return g_err; }
 // problems (streaming chunks), where kernels last a few microseconds and overlapping the next kernel's prologue
 // (barrier init, TMEM allocation, tensor-map prefetch) with the current kernel's tail is worth ~5 % of the latency.
 // At batch 64 it measured 2.5 % slower inside the CUDA graph (r01), so large problems keep plain stream order.
-static int g_pdl_auto = 0;
+// thread-local: each forward call sets it on its own thread right before it enqueues its launches, so two host threads
+// driving two contexts never see each other's choice
+static thread_local int g_pdl_auto = 0;
 void pdl_set_auto(bool on) { g_pdl_auto = on ? 1 : 0; }
 bool pdl_enabled() {
   static int forced = -2;
@@ -36,6 +40,8 @@ bool pdl_enabled() {
 
 cudaError_t raise_max_dyn_smem(const void* func, size_t bytes) {
   static std::map<std::pair<int, const void*>, size_t> cur;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -46,9 +52,9 @@ cudaError_t raise_max_dyn_smem(const void* func, size_t bytes) {
   return e;
 }
 
-static long long g_launches = 0;
-void count_launch() { ++g_launches; }
-long long launch_count() { return g_launches; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

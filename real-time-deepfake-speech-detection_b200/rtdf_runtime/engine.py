@@ -59,6 +59,10 @@ class Engine:
         # shape replaces ~215 launches by one (RTDF_CUDA_GRAPH=0 disables).
         self.use_graph = bool(int(os.environ.get("RTDF_CUDA_GRAPH", "1"))) if use_graph is None else bool(use_graph)
         self._graphs = {}
+        # "auto": streaming chunks (<= 512 frames in flight) use the low-latency weight-streaming kernels;
+        # "throughput": batch-composition-invariant large-batch kernels only (include/rtdf.h rtdf_regime).
+        self.regime = os.environ.get("RTDF_REGIME", "auto")
+        self._regime_set = None
         with torch.cuda.device(self.device):
             native.check(self.lib.rtdf_create(ctypes.byref(self._ctx), self.device.index, ctypes.byref(desc)),
                          "rtdf_create")
@@ -101,14 +105,23 @@ class Engine:
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def _apply_regime(self, regime):
+        regime = regime or self.regime
+        if regime not in native.REGIMES:
+            raise ValueError(f"rtdf: unknown regime {regime!r} (expected one of {sorted(native.REGIMES)})")
+        if regime != self._regime_set:
+            native.check(self.lib.rtdf_set_regime(self._ctx, native.REGIMES[regime]), "rtdf_set_regime")
+            self._regime_set = regime
+        return regime
+
     def _launch_forward(self, wav, B, N, preemph, coef, logits, ws):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         native.check(self.lib.rtdf_forward(self._ctx, native.ptr(wav), B, N, int(bool(preemph)), float(coef),
                                            native.ptr(logits), native.ptr(ws), ws.numel(), None,
                                            ctypes.c_void_p(stream)), "rtdf_forward")
 
-    def _graph_forward(self, wav, B, N, preemph, coef):
-        key = (B, N, bool(preemph), float(coef))
+    def _graph_forward(self, wav, B, N, preemph, coef, regime):
+        key = (B, N, bool(preemph), float(coef), regime)
         ws = self._workspace(B, N)
         entry = self._graphs.get(key)
         if entry is None:
@@ -139,8 +152,11 @@ class Engine:
             raise ValueError(f"rtdf: expected (B,N) waveforms, got shape {tuple(wav.shape)}")
         return wav.to(torch.float32).contiguous()
 
-    def forward(self, wav, preemph=False, coef=0.97, want_taps=False, layer_taps=False):
+    def forward(self, wav, preemph=False, coef=0.97, want_taps=False, layer_taps=False, regime=None):
         """(B,N) fp32 CUDA waveforms -> (B,2) fp32 logits [, taps dict].
+
+        regime: None (the engine's default, ``self.regime``), "auto" or "throughput" (batch-composition-invariant
+        kernels only; what the sharded scoring sweep uses).
 
         layer_taps (with want_taps): also return taps['layers'], (n_layers+1, B, T, 1024) fp32 -- the residual
         stream entering layer 0 and leaving each transformer layer (the I/O of ``encoder.layers.N`` that the
@@ -151,8 +167,9 @@ class Engine:
             out = torch.empty(0, 2, dtype=torch.float32, device=self.device)
             return (out, {}) if want_taps else out
         with torch.cuda.device(self.device):
+            regime = self._apply_regime(regime)
             if self.use_graph and not want_taps and not torch.cuda.is_current_stream_capturing():
-                return self._graph_forward(wav, B, N, preemph, coef)
+                return self._graph_forward(wav, B, N, preemph, coef, regime)
             ws = self._workspace(B, N)
             logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
             taps_struct, taps = None, {}
@@ -178,9 +195,10 @@ class Engine:
                                                ctypes.c_void_p(stream)), "rtdf_forward")
         return (logits, taps) if want_taps else logits
 
-    def frontend(self, wav, preemph=False, coef=0.97):
+    def frontend(self, wav, preemph=False, coef=0.97, regime=None):
         """XLSR_FE.extract_feat: (B,N) -> (B,T,1024) fp32."""
         wav = self._check_wav(wav)
+        self._apply_regime(regime)
         B, N = wav.shape
         T = self.num_frames(N)
         if T < 1:
@@ -200,6 +218,7 @@ class Engine:
             raise ValueError("rtdf: backend expects (B,T,1024) CUDA features")
         feats = feats.to(torch.float32).contiguous()
         B, T, _ = feats.shape
+        self._apply_regime(None)
         with torch.cuda.device(self.device):
             ws = self._workspace(B, max(400, T * 320 + 80))
             logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
@@ -221,12 +240,27 @@ def _fingerprint(module):
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
 
 
+def invalidate(module):
+    """Drop the engine cached on ``module`` so the next forward re-packs the weights.
+
+    ``engine_for`` notices re-assigned parameters, ``load_state_dict`` and in-place ops through the tensors' version
+    counters; writes that bypass them -- ``param.data.normal_()``, ``param.data[...] = ...``, raw pointer writes -- are
+    invisible to it: call ``invalidate(model)`` after such a write."""
+    cached = module.__dict__.pop("_rtdf_engine", None)
+    if cached is not None:
+        cached[1].close()
+
+
 def engine_for(module, backend, n_layers, conformer=None, key_prefix=""):
     """Engine cached on ``module``; rebuilt when any parameter/buffer changed (version counters),
-    when the module moved to another device or when the requested precision changed."""
+    when the module moved to another device or when the requested precision changed.  ``module.rtdf_frozen = True``
+    skips the per-call scan of the ~450 tensors (weights declared final; see ``invalidate``)."""
     if module.training:
         raise RuntimeError("rtdf accelerates the eval-mode scoring forward only: call model.eval() first "
                            "(the reference's scoring callers do: main.py:202, trainer.py:86)")
+    cached = module.__dict__.get("_rtdf_engine")
+    if cached is not None and getattr(module, "rtdf_frozen", False):
+        return cached[1]
     try:
         dev = next(module.parameters()).device
     except StopIteration:
@@ -235,8 +269,7 @@ def engine_for(module, backend, n_layers, conformer=None, key_prefix=""):
         raise RuntimeError("rtdf has no CPU path: move the model to a CUDA device with .to(device)")
     precision = getattr(module, "rtdf_precision", None) or _precision_from_env()
     fp = (_fingerprint(module), str(dev), precision, backend, n_layers)
-    cached = module.__dict__.get("_rtdf_engine")
-    if cached is not None and (getattr(module, "rtdf_frozen", False) or cached[0] == fp):
+    if cached is not None and cached[0] == fp:
         return cached[1]
     if cached is not None:
         cached[1].close()

@@ -14,6 +14,8 @@ c_void_p, c_int, c_float, c_size_t, c_longlong = (ctypes.c_void_p, ctypes.c_int,
 
 BACKEND_AASIST, BACKEND_CONFORMER, BACKEND_NONE = 0, 1, 2
 PREC_BF16, PREC_FP32 = 0, 1
+REGIME_AUTO, REGIME_THROUGHPUT = 0, 1
+REGIMES = {"auto": REGIME_AUTO, "throughput": REGIME_THROUGHPUT}
 ACT_NONE, ACT_GELU, ACT_SWISH, ACT_SELU = 0, 1, 2, 3
 
 
@@ -38,6 +40,7 @@ SIGNATURES = {
     "rtdf_create": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(ModelDesc)]),
     "rtdf_load_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, ctypes.POINTER(ctypes.c_int64), c_int]),
     "rtdf_finalize": (c_int, [c_void_p]),
+    "rtdf_set_regime": (c_int, [c_void_p, c_int]),
     "rtdf_destroy": (None, [c_void_p]),
     "rtdf_last_error": (ctypes.c_char_p, []),
     "rtdf_num_frames": (c_int, [c_int]),
@@ -66,6 +69,9 @@ SIGNATURES = {
                                     ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                     c_int, c_void_p]),
+    "rtdf_conformer_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "rtdf_conformer_glu_dwconv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_int, c_void_p]),
     "rtdf_launch_count": (c_longlong, []),
     "rtdf_debug_gelu_variant": (c_int, [c_int]),
     "rtdf_profile_begin": (c_int, []),

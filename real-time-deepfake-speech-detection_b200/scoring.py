@@ -63,12 +63,15 @@ class ScoringPipeline:
     synchronisation is in ``finish``.  Every batch still crosses PCIe in both directions.
     """
 
-    def __init__(self, model, capacity, batch_size, n_samples, device, preemph=False, coef=0.97, depth=2):
+    def __init__(self, model, capacity, batch_size, n_samples, device, preemph=False, coef=0.97, depth=2,
+                 regime="throughput"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ScoringPipeline runs on CUDA devices only (no CPU path)")
         self.eng = model.engine()
         self.preemph, self.coef = preemph, coef
+        # large-batch kernels only: a score must not depend on the batch (ragged tail) or the shard it lands in
+        self.regime = regime
         self.batch_size, self.n_samples = int(batch_size), int(n_samples)
         self.dev_in = [torch.empty(batch_size, n_samples, dtype=torch.float32, device=self.device) for _ in range(depth)]
         self.ready = [torch.cuda.Event() for _ in range(depth)]
@@ -99,7 +102,7 @@ class ScoringPipeline:
             self.ready[slot].record(self.copy_stream)
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.ready[slot])
-        logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef)
+        logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef, regime=self.regime)
         self.free[slot].record(cur)
         dst = self.scores_dev[self.count:self.count + b]
         dst.copy_(logits[:, 1])                                                          # stays on the device ...
@@ -122,8 +125,11 @@ def score_utterances(model, n_items, load_batch, n_samples, batch_size, device, 
     """Score items [0, n_items) sharded over `world` ranks; returns all scores (fp32, global order) on every rank.
 
     load_batch(lo, hi, out): fills the pinned host tensor `out` (hi-lo, n_samples) with utterances lo..hi-1
-    (the reference's DataLoader role, main.py:200-209).  `model` is one of this package's model classes in
-    eval mode on `device`.
+    (the reference's DataLoader role, main.py:200-209) and returns None -- or returns its own (hi-lo, n_samples) fp32
+    CPU tensor (ideally pinned, e.g. a slice of a resident pool), which is then copied to the device instead of `out`
+    and must stay untouched until this call returns.  `model` is one of this package's model classes in eval mode on
+    `device`.  The forwards run in the throughput regime, so a score does not depend on the batch or shard an utterance
+    lands in: the returned vector is bit-identical for every `world` / `batch_size`.
     """
     lo, hi, per = shard_range(n_items, rank, world)
     pipe = ScoringPipeline(model, max(hi - lo, 1), batch_size, n_samples, device, preemph=preemph, coef=coef, depth=2)
@@ -132,8 +138,8 @@ def score_utterances(model, n_items, load_batch, n_samples, batch_size, device, 
         # 3 host buffers for 2 device slots: push(i) waits for forward(i-2), whose H2D (the last reader of buffer
         # (i-2) % 3 ... and of buffer i % 3 = (i-3) % 3) is then complete
         out = host[i % 3][: b_hi - b_lo]
-        load_batch(b_lo, b_hi, out)
-        pipe.push(out)
+        own = load_batch(b_lo, b_hi, out)
+        pipe.push(out if own is None else own)
     torch.cuda.current_stream(torch.device(device)).synchronize()
     return gather_scores(pipe.device_scores(), n_items, per, group)
 

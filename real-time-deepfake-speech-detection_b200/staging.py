@@ -54,7 +54,7 @@ class UtteranceStager:
             "dev_off": torch.empty(self.batch_size + 1, dtype=torch.int64, device=self.device),
             "dev_start": torch.empty(self.batch_size, dtype=torch.int32, device=self.device),
             "out": torch.empty(self.batch_size, self.duration, dtype=torch.float32, device=self.device),
-            "copied": torch.cuda.Event(), "free": torch.cuda.Event(),
+            "copied": torch.cuda.Event(), "free": torch.cuda.Event(), "outstanding": False,
         } for _ in range(slots)]
         self.copy_stream = torch.cuda.Stream(self.device)
         self.cur = 0
@@ -68,7 +68,11 @@ class UtteranceStager:
             raise ValueError(f"batch of {B} utterances (1..{self.batch_size} supported)")
         slot = self.slots[self.cur]
         self.cur = (self.cur + 1) % len(self.slots)
+        if slot["outstanding"]:
+            raise RuntimeError("UtteranceStager: slot re-staged while its previous ticket is outstanding -- call "
+                               "release(ticket) after the forward that consumed take(ticket) (or raise `slots`)")
         slot["free"].synchronize()              # the forward that consumed this slot's `out` has finished
+        slot["outstanding"] = True
         flat = [np.asarray(u, dtype=np.float32).reshape(-1) if not torch.is_tensor(u)
                 else u.detach().to(torch.float32).reshape(-1).numpy() for u in utterances]
         starts = crop_starts([len(u) for u in flat], self.duration, self.random_start, self.rng)
@@ -104,7 +108,12 @@ class UtteranceStager:
         return slot["out"][:B]
 
     def release(self, ticket):
+        """Call after enqueueing the work that reads ``take(ticket)`` (same stream): records the event the next
+        ``stage`` into this slot waits for, so the slot's pinned / device buffers are not overwritten while the copy,
+        the fit kernel or the forward may still be reading them.  A slot whose ticket was not released cannot be
+        staged again (``stage`` raises)."""
         ticket[0]["free"].record(torch.cuda.current_stream(self.device))
+        ticket[0]["outstanding"] = False
 
 
 def fit_duration(packed, offsets, duration, starts=None, preemph=None):

@@ -1,8 +1,10 @@
 """Block- and end-to-end parity of the CUDA path against the CPU oracle and the committed golden
 vectors (which were produced by the reference's own model files, see oracle/check_against_reference.py).
 
-Tolerances (BASELINE.json north_star): max |logit diff| <= 1e-4 in fp32 mode, <= 1e-2 in bf16 mode;
-GraphPool node selection bit-exact when fed identical fp32 inputs (rows with distinct scores)."""
+Tolerances: BASELINE.json north_star asks for max |logit diff| <= 1e-4 in fp32 mode and <= 1e-2 in bf16 mode.  On
+random-init weights the logits are O(0.1-0.5), so the bf16 bound asserted here is 10x tighter than that: 1e-3 for the
+AASIST models (measured 6e-5) and 5e-3 for the Conformer models (measured 1.1e-3).  GraphPool node selection is
+bit-exact when fed identical fp32 inputs (rows with distinct scores); in bf16 mode the agreement rate is reported."""
 import os
 
 import numpy as np
@@ -10,7 +12,13 @@ import torch
 
 from tests.util import ROOT, build_pair
 
-TOL = {"fp32": 1e-4, "bf16": 1e-2}
+TOL = {"fp32": 1e-4, "bf16": 1e-3}              # AASIST models
+TOL_CONFORMER = {"fp32": 1e-4, "bf16": 5e-3}
+FEATS_TOL = {"fp32": 2e-4, "bf16": 0.05}        # LayerNorm-ed XLS-R features are O(1); bf16 through 24 layers: 0.033
+
+
+def tol_for(kind, precision):
+    return (TOL_CONFORMER if kind in ("ConformerModel", "MyModel") else TOL)[precision]
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -48,7 +56,7 @@ def check_frontend_block(precision="fp32", B=2, N=16000, kind="XLSR_AASIST", **k
     d = float((got - ref).abs().max())
     rel = d / float(ref.abs().max())
     res = {"max_abs": d, "rel_to_max": rel, "ref_absmean": float(ref.abs().mean())}
-    assert d <= (2e-4 if precision == "fp32" else 0.08), res   # LayerNorm-ed features are O(1); bf16 through 24 layers
+    assert d <= FEATS_TOL[precision], res
     return res
 
 
@@ -61,7 +69,7 @@ def check_e2e(kind="XLSR_AASIST", precision="fp32", B=2, N=16000, **kw):
     d = float((got - ref).abs().max())
     res = {"max_dlogit": d, "ref0": ref[0].tolist(), "got0": got[0].tolist()}
     assert got.shape == (B, 2) and got.dtype == torch.float32
-    assert d <= TOL[precision], res
+    assert d <= tol_for(kind, precision), res
     return res
 
 
@@ -84,9 +92,14 @@ def check_golden(name, precision="fp32"):
     if taps is not None:
         fh = torch.from_numpy(g["feats_head"])
         res["feats_head_maxdiff"] = float((taps["feats"][:, :4, :16].cpu() - fh).abs().max())
-        res["idx_S_equal"] = bool((taps["idx_S"].cpu().long() == torch.from_numpy(g["idx_S"])).all())
-        res["idx_T_equal"] = bool((taps["idx_T"].cpu().long() == torch.from_numpy(g["idx_T"])).all())
-    assert d <= TOL[precision], res
+        eq_S = taps["idx_S"].cpu().long() == torch.from_numpy(g["idx_S"])
+        eq_T = taps["idx_T"].cpu().long() == torch.from_numpy(g["idx_T"])
+        res["idx_S_equal"], res["idx_T_equal"] = bool(eq_S.all()), bool(eq_T.all())
+        res["idx_agreement_rate"] = float(torch.cat([eq_S.flatten(), eq_T.flatten()]).float().mean())
+        assert res["feats_head_maxdiff"] <= FEATS_TOL[precision], res
+        if precision == "fp32":     # fp32 features differ by ~1e-6 from the reference's: same nodes, same order
+            assert res["idx_S_equal"] and res["idx_T_equal"], res
+    assert d <= tol_for(kind, precision), res
     return res
 
 
@@ -115,4 +128,30 @@ def check_ragged_and_quirks(precision="fp32"):
     solo = torch.cat([eng.forward(x[i:i + 1].cuda(), preemph=True).cpu() for i in range(2)])
     res["batch_invariance"] = float((solo - got).abs().max())
     assert res["batch_invariance"] == 0.0, res
+    return res
+
+
+def check_timed_configuration(B=64, N=64000, rows=(0, 31, 63), pair=2):
+    """The configuration bench.py times (BASELINE.json configs[2]: XLSR-AASIST, 24 layers, bf16, batch 64, 4 s):
+      * rows 0 / 31 / 63 of the batch against the CPU oracle (1e-3);
+      * every row bit-equal to the same utterance scored in a batch of `pair` (throughput regime: the kernels chosen
+        do not depend on the batch size -- what the sharded sweep's ragged tail and 1/2/4/8-GPU equality rest on);
+      * the default (auto) regime at batch `pair` -- streaming-chunk kernels -- within 1e-3 of the same scores."""
+    ora, prod = build_pair("XLSR_AASIST", "bf16")
+    x = _waves(B, N, seed=4242)
+    eng = prod.engine()
+    xd = x.cuda()
+    big = eng.forward(xd, regime="throughput").cpu()
+    with torch.no_grad():
+        ref = ora(x[list(rows)])
+    res = {"max_dlogit_vs_oracle": float((big[list(rows)] - ref).abs().max())}
+    assert res["max_dlogit_vs_oracle"] <= TOL["bf16"], res
+    small = torch.cat([eng.forward(xd[i:i + pair], regime="throughput").cpu() for i in range(0, B, pair)])
+    res["batch_composition_max_diff"] = float((small - big).abs().max())
+    assert torch.equal(small, big), res
+    auto = torch.cat([eng.forward(xd[i:i + pair], regime="auto").cpu() for i in range(0, 8, pair)])
+    res["auto_regime_max_diff"] = float((auto - big[:8]).abs().max())
+    assert res["auto_regime_max_diff"] <= TOL["bf16"], res
+    again = eng.forward(xd, regime="throughput").cpu()
+    assert torch.equal(again, big), "forward at the timed batch is not deterministic"
     return res

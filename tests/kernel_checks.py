@@ -250,19 +250,25 @@ def _split(t):
     return hi, (t - hi.float()).to(torch.bfloat16)
 
 
-def check_conv_planes_tc(nsplit=3):
+CONV_PLANES_CASES = [  # (kind, ci, co, B, W)
+    ("conv1", 32, 32, 2, 16), ("conv1", 32, 64, 1, 66), ("conv1", 64, 64, 2, 66), ("conv2", 32, 32, 2, 66),
+    ("conv2", 64, 64, 3, 67), ("ds", 32, 64, 2, 66), ("lin", 64, 128, 2, 66), ("lin", 128, 64, 2, 16),
+    ("conv2", 64, 64, 1, 96),
+]
+# the timed configuration: B = 64, T' = 66 -> 64 * 44 * 68 = 191,488 plane rows = 1,496 row tiles on 148 persistent CTAs
+CONV_PLANES_CASES_TIMED = [("conv1", 64, 64, 64, 66), ("conv1", 32, 64, 64, 66), ("conv2", 64, 64, 64, 66),
+                           ("conv2", 32, 32, 64, 66), ("ds", 32, 64, 64, 66), ("lin", 64, 128, 64, 66),
+                           ("lin", 128, 64, 64, 66)]
+
+
+def check_conv_planes_tc(nsplit=3, cases=None):
     """Shifted-row tcgen05 conv on zero-padded channels-last planes against F.conv2d (fp32) for the three
     Residual_block convolutions (aasist_modules.py:340-397) and the 1x1 attention convs (xlsr_aasist.py:103)."""
     import ctypes
     g = torch.Generator().manual_seed(11)
     out = {}
     Hp = 44
-    cases = [  # (kind, ci, co, B, W)
-        ("conv1", 32, 32, 2, 16), ("conv1", 32, 64, 1, 66), ("conv1", 64, 64, 2, 66), ("conv2", 32, 32, 2, 66),
-        ("conv2", 64, 64, 3, 67), ("ds", 32, 64, 2, 66), ("lin", 64, 128, 2, 66), ("lin", 128, 64, 2, 16),
-        ("conv2", 64, 64, 1, 96),
-    ]
-    for kind, ci, co, B, W in cases:
+    for kind, ci, co, B, W in (cases or CONV_PLANES_CASES):
         Wp = W + 2
         rows = B * Hp * Wp
         Hin = 43 if kind == "conv2" else 42
@@ -331,16 +337,32 @@ def _conv_ref(x, w, b, gamma, beta, stride):
     return F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))
 
 
-def check_conv1d_tc(variants=(512, 513)):
+CONV1D_SHAPES = ((2, 799, 3), (1, 403, 2), (3, 130, 3), (2, 12799, 3))
+# the timed configuration: conv-1 (64 x 12,799 -> 6,399 frames: 3,200 row tiles, 1,600 CTA pairs) and conv-5 (64 x 799 -> 399)
+CONV1D_SHAPES_TIMED = ((64, 12799, 3), (64, 799, 2))
+
+
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+
+
+def check_conv1d_tc(variants=(512, 513), shapes=CONV1D_SHAPES):
     g = torch.Generator().manual_seed(4)
     out = {}
-    for B, L, k in ((2, 799, 3), (1, 403, 2), (3, 130, 3), (2, 12799, 3)):
+    for B, L, k in shapes:
         x = torch.randn(B, L, 512, generator=g).to(torch.bfloat16)
         w = (torch.randn(512, 512, k, generator=g) / math.sqrt(512 * k)).to(torch.bfloat16)
         b = torch.randn(512, generator=g) * 0.1
         gamma = 1 + 0.1 * torch.randn(512, generator=g)
         beta = 0.1 * torch.randn(512, generator=g)
-        ref = _conv_ref(x.float(), w.float(), b, gamma, beta, 2)
+        if B * L > 100000:       # 0.6 TFLOP of fp32 reference: plain PyTorch fp32 ops on the GPU (TF32 off), in slices
+            _no_tf32()
+            ref = torch.cat([_conv_ref(x[i:i + 8].to(DEV).float(), w.to(DEV).float(), b.to(DEV), gamma.to(DEV),
+                                       beta.to(DEV), 2).cpu() for i in range(0, B, 8)])
+        else:
+            ref = _conv_ref(x.float(), w.float(), b, gamma, beta, 2)
         Lo = ref.shape[1]
         wp = w.permute(0, 2, 1).contiguous().to(DEV)               # [co][k][ci]
         for v in variants:
@@ -355,14 +377,21 @@ def check_conv1d_tc(variants=(512, 513)):
 
 def _posconv_ref(x, w, bias):
     B, T, C = x.shape
+    if B * T > 4000:        # 0.2 TFLOP: plain PyTorch fp32 ops on the GPU (TF32 off)
+        _no_tf32()
+        x, w, bias = x.to(DEV), w.to(DEV), bias.to(DEV)
     y = F.conv1d(x.transpose(1, 2), w, bias, padding=64, groups=16)[:, :, :T]
-    return x + F.gelu(y).transpose(1, 2)
+    return (x + F.gelu(y).transpose(1, 2)).cpu()
 
 
-def check_posconv():
+POSCONV_SHAPES = ((2, 199), (1, 49), (2, 130), (3, 128), (2, 257), (1, 1), (2, 520))
+POSCONV_SHAPES_TIMED = ((64, 199),)      # 1,024 (utterance, group) items on 148 persistent CTAs: ~7 items per CTA
+
+
+def check_posconv(shapes=POSCONV_SHAPES):
     g = torch.Generator().manual_seed(5)
     out = {}
-    for B, T in ((2, 199), (1, 49), (2, 130), (3, 128), (2, 257), (1, 1), (2, 520)):
+    for B, T in shapes:
         x = torch.randn(B, T, 1024, generator=g)
         w = torch.randn(1024, 64, 128, generator=g) / math.sqrt(64 * 128)
         bias = torch.randn(1024, generator=g) * 0.1
@@ -391,10 +420,16 @@ def _attn_ref(qkv, B, T, H):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
 
 
-def check_attention(impls=(0, 1)):
+ATTN_SHAPES = ((2, 199, 16), (1, 49, 16), (2, 201, 4), (1, 128, 2), (1, 256, 2), (3, 17, 1))
+# the timed configuration (BASELINE configs[2]): 2,048 (utterance, head, query tile) items on <= 148 persistent CTAs, so
+# every CTA loops ~14 times over its smem ring / TMEM buffers / mbarrier phases
+ATTN_SHAPES_TIMED = ((64, 199, 16), (64, 201, 16))
+
+
+def check_attention(impls=(0, 1), shapes=ATTN_SHAPES):
     g = torch.Generator().manual_seed(6)
     out = {}
-    for B, T, H in ((2, 199, 16), (1, 49, 16), (2, 201, 4), (1, 128, 2), (1, 256, 2), (3, 17, 1)):
+    for B, T, H in shapes:
         qkv = torch.randn(B * T, 3 * H * 64, generator=g)
         qkv[:, : H * 64] *= 0.25
         ref32 = _attn_ref(qkv, B, T, H)
@@ -507,4 +542,67 @@ def check_gat_rows(impl=0):
         d = max(float((o.cpu() - torch.cat([r1, r2], 1)).abs().max()), float((mo.cpu() - rm.reshape(B, DO)).abs().max()))
         out[f"hsgal_B{B}_n{n1}+{n2}_D{D}"] = d
         assert d <= tol, out
+    return out
+
+
+def check_conformer_attention(is_bf16=1, impl=0, shapes=((2, 50, 4, 36), (2, 200, 4, 36), (1, 202, 4, 36), (2, 17, 2, 36))):
+    """Shaw relative-position MHSA of lucidrains' ConformerBlock (instantiated at reference
+    models/conformer_baseline.py:16-18; oracle/conformer_block_ref.py Attention) from a packed [q|k|v] matrix."""
+    from oracle.conformer_block_ref import Attention
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for B, n, heads, dh in shapes:
+        E = heads * dh
+        att = Attention(E, heads=heads, dim_head=dh).eval()
+        with torch.no_grad():
+            att.rel_pos_emb.weight.copy_(torch.randn(1025, dh, generator=g) * 0.5)
+        qkv = torch.randn(B * n, 3 * E, generator=g)
+        if is_bf16:
+            qkv = qkv.to(torch.bfloat16).float()
+        q, k, v = (qkv[:, i * E:(i + 1) * E].reshape(B, n, heads, dh).transpose(1, 2) for i in range(3))
+        dots = torch.einsum("bhid,bhjd->bhij", q, k) * att.scale
+        seq = torch.arange(n)
+        dist = (seq[:, None] - seq[None, :]).clamp(-512, 512) + 512
+        rel = att.rel_pos_emb.weight[dist]
+        dots = dots + torch.einsum("bhnd,nrd->bhnr", q, rel) * att.scale
+        ref = torch.einsum("bhij,bhjd->bhid", dots.softmax(-1), v).transpose(1, 2).reshape(B * n, E)
+        dt = torch.bfloat16 if is_bf16 else torch.float32
+        o = torch.zeros(B * n, E, dtype=dt, device=DEV)
+        call("rtdf_conformer_attention", P(dev(qkv.to(dt))), P(dev(att.rel_pos_emb.weight.detach())), P(o), B, n, heads, dh,
+             is_bf16, impl, stream())
+        d = float((o.float().cpu() - ref).abs().max())
+        out[f"B{B}_n{n}_h{heads}_bf16{is_bf16}_impl{impl}"] = d
+        assert d <= (0.03 if is_bf16 else 2e-5), out     # bf16: rel-pos table / P / output rounded to bf16, |out| <~ 3
+    return out
+
+
+def check_conformer_glu_dwconv(is_bf16=1, shapes=((2, 50, 288, 31), (2, 200, 288, 31), (1, 313, 288, 31), (3, 7, 288, 31),
+                                                   (2, 64, 64, 15))):
+    """GLU -> depth-wise conv ("same" padding) -> BatchNorm1d (eval) -> Swish of the Conformer convolution module
+    (oracle/conformer_block_ref.py ConformerConvModule.net[3:7])."""
+    from oracle.conformer_block_ref import ConformerConvModule
+    g = torch.Generator().manual_seed(22)
+    out = {}
+    for B, n, inner, k in shapes:
+        mod = ConformerConvModule(inner // 2, expansion_factor=2, kernel_size=k).eval()
+        glu, dw, bn, swish = mod.net[3], mod.net[4], mod.net[5], mod.net[6]
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.randn(inner, generator=g) * 0.1)
+            bn.running_var.copy_(torch.rand(inner, generator=g) + 0.5)
+            bn.weight.copy_(1 + 0.1 * torch.randn(inner, generator=g))
+            bn.bias.copy_(0.1 * torch.randn(inner, generator=g))
+        x = torch.randn(B * n, 2 * inner, generator=g)
+        if is_bf16:
+            x = x.to(torch.bfloat16).float()
+        with torch.no_grad():
+            ref = swish(bn(dw(glu(x.reshape(B, n, 2 * inner).transpose(1, 2))))).transpose(1, 2).reshape(B * n, inner)
+        s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        t = bn.bias - bn.running_mean * s
+        dt = torch.bfloat16 if is_bf16 else torch.float32
+        o = torch.zeros(B * n, inner, dtype=dt, device=DEV)
+        call("rtdf_conformer_glu_dwconv", P(dev(x.to(dt))), P(o), B, n, inner, k, P(dev(dw.conv.weight.detach().reshape(inner, k))),
+             P(dev(dw.conv.bias.detach())), P(dev(s.detach())), P(dev(t.detach())), is_bf16, stream())
+        d = float((o.float().cpu() - ref).abs().max())
+        out[f"B{B}_n{n}_c{inner}_k{k}_bf16{is_bf16}"] = d
+        assert d <= (0.03 if is_bf16 else 2e-5), out
     return out

@@ -45,6 +45,10 @@ def test_golden_vectors_from_reference(name, precision):
     ec.check_golden(name, precision=precision)
 
 
+def test_timed_configuration_parity_and_batch_invariance():
+    ec.check_timed_configuration()
+
+
 def test_ragged_batches_preemphasis_determinism():
     ec.check_ragged_and_quirks(precision="fp32")
 

@@ -76,3 +76,41 @@ def test_graph_pool_bit_exact_topk():
 @pytest.mark.parametrize("impl", [0, 1])
 def test_graph_attention_rows(impl):
     kc.check_gat_rows(impl)
+
+
+# ---- the timed configuration (BASELINE.json configs[2]: batch 64, 4 s): every persistent kernel loops over many more
+# ---- items than there are SMs, so smem-ring wrap-around, TMEM double-buffer reuse and mbarrier phase flips are compared
+# ---- with the fp32 reference too ("What's weak" 1)
+def test_attention_at_timed_batch():
+    kc.check_attention(impls=(0,), shapes=kc.ATTN_SHAPES_TIMED)
+
+
+def test_posconv_at_timed_batch():
+    kc.check_posconv(shapes=kc.POSCONV_SHAPES_TIMED)
+
+
+def test_conv_planes_tcgen05_at_timed_batch():
+    kc.check_conv_planes_tc(nsplit=3, cases=kc.CONV_PLANES_CASES_TIMED)
+
+
+@pytest.mark.parametrize("variant", [515, 516])
+def test_conv1d_implicit_gemm_at_timed_batch(variant):
+    kc.check_conv1d_tc(variants=(variant,), shapes=kc.CONV1D_SHAPES_TIMED)
+
+
+# ---- Conformer block kernels (lucidrains ConformerBlock, reference models/conformer_baseline.py:16-18) ----
+@pytest.mark.parametrize("is_bf16,impl", [(0, 0), (1, 0), (1, 1)])
+def test_conformer_relpos_attention(is_bf16, impl):
+    kc.check_conformer_attention(is_bf16=is_bf16, impl=impl)
+
+
+def test_conformer_attention_beyond_tensor_core_envelope():
+    # n = 313 tokens: impl 1 (what the forward uses) switches to the SIMT kernel; impl 0 reports "unsupported"
+    kc.check_conformer_attention(is_bf16=1, impl=1, shapes=((1, 313, 4, 36),))
+    with pytest.raises(RuntimeError):
+        kc.check_conformer_attention(is_bf16=1, impl=0, shapes=((1, 313, 4, 36),))
+
+
+@pytest.mark.parametrize("is_bf16", [0, 1])
+def test_conformer_glu_depthwise_conv(is_bf16):
+    kc.check_conformer_glu_dwconv(is_bf16=is_bf16)

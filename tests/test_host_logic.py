@@ -124,3 +124,40 @@ def test_two_rank_gloo_gather_restores_global_order(n_items):
     mp.spawn(_gather_worker, args=(world, port, n_items, ret), nprocs=world, join=True)
     expect = [i * 0.5 for i in range(n_items)]
     assert ret[0] == expect and ret[1] == expect
+
+
+def test_load_pretrained_fairseq_style_checkpoint(tmp_path, monkeypatch):
+    """The reference loads ``xlsr2_300m.pt`` through fairseq (models/fe.py:11-15): a pickled ``{'model': state_dict, ...}``
+    that also carries the pre-training heads.  Here the path comes from $RTDF_XLSR_CKPT; heads are dropped, every XLS-R
+    key must be present, a plain state-dict file works too."""
+    import torch
+    w2v = pkg("models.wav2vec2_params")
+    fe = pkg("models.fe")
+    skeleton = w2v.Wav2Vec2Model()
+    keys = list(skeleton.state_dict().keys())
+    # every tensor is a stride-0 expansion of one element, so the 1.2 GB checkpoint is a few hundred KB on disk
+    sd = {k: torch.full((1,), (i + 1) / 1024.0).expand(skeleton.state_dict()[k].shape) for i, k in enumerate(keys)}
+    heads = {"quantizer.vars": torch.zeros(1, 640, 384), "quantizer.weight_proj.weight": torch.zeros(640, 512),
+             "project_q.weight": torch.zeros(768, 768), "final_proj.bias": torch.zeros(768)}
+    path = str(tmp_path / "xlsr2_300m.pt")
+    torch.save({"model": {**sd, **heads}, "cfg": {"model": {"_name": "wav2vec2"}}, "args": None}, path)
+    monkeypatch.setenv("RTDF_XLSR_CKPT", path)
+    m = fe.XLSR_FE("cpu")
+    got = m.model.state_dict()
+    assert list(got.keys()) == keys                       # no pre-training head leaked into the module
+    for i, k in enumerate(keys):
+        assert bool((got[k] == (i + 1) / 1024.0).all()), k
+    # truncated student (fe.py:53-90) from the same checkpoint: layers selected after the load
+    s = fe.My_XLSR_FE("cpu", num_layers=2, order="last")
+    want = (keys.index("encoder.layers.23.fc1.bias") + 1) / 1024.0
+    assert bool((s.model.encoder.layers[1].fc1.bias == want).all())
+    # plain state dict (no 'model' wrapper)
+    plain = str(tmp_path / "plain.pt")
+    torch.save(sd, plain)
+    w2v.load_pretrained(skeleton, plain)
+    assert bool((skeleton.post_extract_proj.bias == (keys.index("post_extract_proj.bias") + 1) / 1024.0).all())
+    # a checkpoint that lacks XLS-R keys fails loudly
+    broken = str(tmp_path / "broken.pt")
+    torch.save({"model": {k: v for k, v in sd.items() if "layers.3." not in k}}, broken)
+    with pytest.raises(RuntimeError, match="lacks XLS-R keys"):
+        w2v.load_pretrained(skeleton, broken)

@@ -417,6 +417,10 @@ def run_b200(args):
         def load_batch(b_lo, b_hi, out):
             return pool[b_lo - lo:b_hi - lo]                         # zero-copy: the pinned slice goes straight to H2D
 
+        # one untimed forward per batch shape of this shard (full batches + the ragged tail): CUDA-graph capture and
+        # allocator warm-up are one-time costs a 180 k-utterance sweep amortises and an 8 k one would not
+        for size in sorted({b_hi - b_lo for b_lo, b_hi in scoring.batch_ranges(lo, hi, B)}):
+            eng.forward(inputs[0][:size], regime="throughput")
         barrier()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()

@@ -41,6 +41,10 @@ def build(verbose=True):
                 names.append(os.path.join(sub, f) if sub else f)
     tmp = ARCHIVE + ".tmp"
     with zipfile.ZipFile(tmp, "w", zipfile.ZIP_DEFLATED) as z:
+        for sub in SUBDIRS:
+            if sub:   # explicit directory entries: zipimport only treats `data/` (no __init__.py in the reference) as a
+                      # namespace-package portion when the archive lists the directory itself
+                z.writestr(zipfile.ZipInfo(sub + "/", date_time=(2020, 1, 1, 0, 0, 0)), b"")
         for n in names:
             info = zipfile.ZipInfo(n, date_time=(2020, 1, 1, 0, 0, 0))   # reproducible archive
             info.compress_type = zipfile.ZIP_DEFLATED

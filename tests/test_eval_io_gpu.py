@@ -70,6 +70,11 @@ def test_stager_double_buffering_matches_oracle():
     assert st.h2d_bytes < sum(len(b) for b in batches) * D * 4 + 4096     # never more than `duration` samples per utterance
     with pytest.raises(ValueError):
         st.stage([])
+    st2 = staging.UtteranceStager(D, B, "cuda")
+    st2.stage(batches[0])
+    st2.stage(batches[1])
+    with pytest.raises(RuntimeError, match="outstanding"):
+        st2.stage(batches[2])                      # both slots still hold unreleased tickets
 
 
 def test_score_sink_matches_trainer_test_accumulators():
@@ -154,8 +159,14 @@ def test_scoring_pipeline_matches_direct_forward_bit_exactly():
     _, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=1, order="first")
     N, B = 16000, 4
     x = O.synth_waveforms(11, N, seed=5)
+    eng = prod.engine()
     with torch.no_grad():
-        want = torch.cat([prod(x[i:i + B].cuda())[:, 1].cpu() for i in range(0, 11, B)])
+        # the pipeline pins the throughput regime (batch-composition-invariant kernels, include/rtdf.h rtdf_regime)
+        want = torch.cat([eng.forward(x[i:i + B].cuda(), regime="throughput")[:, 1].cpu() for i in range(0, 11, B)])
+        auto = torch.cat([prod(x[i:i + B].cuda())[:, 1].cpu() for i in range(0, 11, B)])   # model(x): streaming kernels
+    assert (auto - want).abs().max() <= 1e-3          # bf16: the two regimes differ at rounding level only
+    one_batch = eng.forward(x.cuda(), regime="throughput")[:, 1].cpu()
+    assert torch.equal(one_batch, want)               # ... and the throughput regime does not see the batching at all
     pipe = scoring.ScoringPipeline(prod, 11, B, N, "cuda")
     for i in range(0, 11, B):
         pipe.push(x[i:i + B].pin_memory())
@@ -169,3 +180,6 @@ def test_scoring_pipeline_matches_direct_forward_bit_exactly():
         out.copy_(x[lo:hi])
     all_scores = scoring.score_utterances(prod, 11, load, N, B, "cuda")
     assert torch.equal(all_scores.cpu(), want)
+    pool = x.pin_memory()
+    zero_copy = scoring.score_utterances(prod, 11, lambda lo, hi, out: pool[lo:hi], N, 3, "cuda")   # other batch size
+    assert torch.equal(zero_copy.cpu(), want)

@@ -111,6 +111,14 @@ int rtdf_wave_layernorm(const float* x, float* y, int batch, int n, float eps, v
 int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w_tapmajor /*[10][512]*/, const float* bias,
                        const float* gamma, const float* beta, float eps, float* out_f32 /*or NULL*/,
                        void* out_bf16 /*or NULL*/, void* stream);
+/* conv-0 of the feature encoder in fairseq's extractor_mode="default" (wav2vec2-base style; the alternative SURVEY.md
+ * App. A.2 step 1 describes): Conv1d(1, 512, 10, stride 5, bias optional -- NULL when conv_bias=False) ->
+ * GroupNorm(512 groups, 512 channels), i.e. per-(utterance, channel) statistics over time -> GELU; channels-last output
+ * (B, L1, 512).  workspace: rtdf_conv0_gn_workspace_floats(batch, n) floats of device scratch. */
+long long rtdf_conv0_gn_workspace_floats(int batch, int n);
+int rtdf_conv0_gn_gelu(const float* wav, int batch, int n, const float* w_tapmajor /*[10][512]*/, const float* bias,
+                       const float* gamma, const float* beta, float eps, float* workspace, float* out_f32 /*or NULL*/,
+                       void* out_bf16 /*or NULL*/, void* stream);
 int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
                         const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream);
 /* D = act(A W^T + bias) * scale + resid.  A: (M,K) bf16, W: (N,K) bf16.  variant: tile width 64|128|256 (one CTA

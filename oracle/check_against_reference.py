@@ -33,6 +33,11 @@ REF = "/root/reference"
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# what the stand-in for fairseq's checkpoint loader builds: XLS-R's layout, or the wav2vec2-base style one (the
+# reference's fe.py takes whatever architecture the checkpoint's config describes)
+SHIM_EXTRACTOR = {"extractor_mode": "layer_norm", "conv_bias": True}
+
+
 def install_shims():
     from oracle.conformer_block_ref import ConformerBlock
     from oracle.wav2vec2_ref import FairseqLikeWav2Vec2
@@ -41,7 +46,7 @@ def install_shims():
     cu = types.ModuleType("fairseq.checkpoint_utils")
 
     def load_model_ensemble_and_task(paths, *a, **k):
-        return [FairseqLikeWav2Vec2()], None, None
+        return [FairseqLikeWav2Vec2(**SHIM_EXTRACTOR)], None, None
 
     cu.load_model_ensemble_and_task = load_model_ensemble_and_task
     fairseq.checkpoint_utils = cu
@@ -93,14 +98,21 @@ def main():
         ("student_mid4_aasist_n16000_b2", xa.My_XLSR_AASIST, "My_XLSR_AASIST", {"num_layers": 4, "order": "middle"}, 2, 16000),
         ("conformer_n64600_b1", cb.Model, "ConformerModel", {}, 1, 64600),
         ("conformer_n16000_b2", cb.Model, "ConformerModel", {}, 2, 16000),
+        # group-norm feature encoder (fairseq extractor_mode="default", conv_bias=False) under the reference's own classes
+        ("student2_aasist_groupnorm_n16000_b2", xa.My_XLSR_AASIST, "My_XLSR_AASIST",
+         {"num_layers": 2, "order": "first", "extractor_mode": "default"}, 2, 16000),
+        ("student2_aasist_groupnorm_n64600_b1", xa.My_XLSR_AASIST, "My_XLSR_AASIST",
+         {"num_layers": 2, "order": "first", "extractor_mode": "default"}, 1, 64600),
     ]
     for name, rcls, okind, kw, B, N in cases:
         seed = 1024
+        gn = kw.get("extractor_mode") == "default"
+        SHIM_EXTRACTOR.update(extractor_mode="default" if gn else "layer_norm", conv_bias=not gn)
         # Weights come from the ORACLE's seeded constructor (reproducible on the GPU box, where
         # /root/reference does not exist) and are loaded into the reference's own model with
         # strict=True: identical keys/shapes is part of the check.
         ora = O.build(okind, seed=seed, **kw)
-        ref = ref_build(rcls, seed + 7, **kw)
+        ref = ref_build(rcls, seed + 7, **{k: v for k, v in kw.items() if k != "extractor_mode"})
         ref.load_state_dict(ora.state_dict(), strict=True)
         x = O.synth_waveforms(B, N, seed=2021)
         with torch.no_grad():
@@ -117,6 +129,7 @@ def main():
         if "idx_S" in taps:
             results[name].update(idx_S=taps["idx_S"].numpy().astype(np.int64), idx_T=taps["idx_T"].numpy().astype(np.int64))
 
+    SHIM_EXTRACTOR.update(extractor_mode="layer_norm", conv_bias=True)
     # student Conformer: shipped forward raises TypeError (conformer_baseline.py:98)
     stu = ref_build(cb.MyModel, 1024, num_layers=2)
     # ... and with the call fixed to one argument it matches the oracle

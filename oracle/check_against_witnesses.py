@@ -80,6 +80,28 @@ def main():
     d = float((a - b).abs().max())
     print(f"oracle vs torchaudio.wav2vec2_xlsr_300m: shape {tuple(a.shape)} max|diff| = {d:.3e} (|x| mean {float(a.abs().mean()):.3f})")
     assert d < 5e-5
+    # extractor_mode="default" (wav2vec2-base style: GroupNorm(512, 512) after conv-0 only, no conv bias): the conv stack of
+    # the oracle against torchaudio's "group_norm" feature extractor (TA:components.py:564-574)
+    from torchaudio.models.wav2vec2 import components as tac
+    from oracle.wav2vec2_ref import CONV_LAYERS, ConvFeatureExtractionModel
+    torch.manual_seed(1)
+    fe = ConvFeatureExtractionModel(mode="default", conv_bias=False).eval()
+    with torch.no_grad():
+        fe.conv_layers[0][2].weight.uniform_(0.8, 1.2)
+        fe.conv_layers[0][2].bias.normal_(0, 0.1)
+    ta_fe = tac._get_feature_extractor("group_norm", list(CONV_LAYERS), bias=False).eval()
+    sd = {}
+    for k, v in fe.state_dict().items():
+        i, j, name = k.split(".")[1], k.split(".")[2], k.split(".")[-1]
+        sd[f"conv_layers.{i}.conv.{name}" if j == "0" else f"conv_layers.{i}.layer_norm.{name}"] = v
+    ta_fe.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        a = fe(x).transpose(1, 2)
+        b = ta_fe(x, None)[0]
+    d = float((a - b).abs().max())
+    print(f"oracle conv stack (group-norm mode) vs torchaudio group_norm feature extractor: shape {tuple(a.shape)} "
+          f"max|diff| = {d:.3e}")
+    assert d < 2e-5
     if args.hf:
         from torchaudio.models.wav2vec2.utils import import_huggingface_model
         from transformers import Wav2Vec2Config, Wav2Vec2Model

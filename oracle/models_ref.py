@@ -26,9 +26,13 @@ def middle_indices(array_length, number_of_middle_elements):
 class XLSR_FE(nn.Module):
     """fe.py:8-24 -- wraps the fairseq model; extract_feat returns ['x']."""
 
-    def __init__(self, device="cpu"):
+    def __init__(self, device="cpu", extractor_mode=None, conv_bias=None, **_):
         super().__init__()
-        self.model = FairseqLikeWav2Vec2().to(device)
+        # what fairseq would build from the checkpoint's config: XLS-R is extractor_mode="layer_norm", conv_bias=True;
+        # "default" is the wav2vec2-base style group-norm feature encoder (SURVEY.md App. A.2 step 1)
+        mode = extractor_mode or "layer_norm"
+        self.model = FairseqLikeWav2Vec2(extractor_mode=mode,
+                                         conv_bias=(mode == "layer_norm") if conv_bias is None else conv_bias).to(device)
         self.out_dim = 1024
 
     def extract_feat(self, x):
@@ -47,7 +51,7 @@ class My_XLSR_FE(XLSR_FE):
         custom_order = kwargs.get("custom_order", None)
         if num_layers < 1 or num_layers > 24:                               # fe.py:60-62
             raise ValueError("Number of layers must be at least 1 and at most 24.")
-        super().__init__(device)
+        super().__init__(device, kwargs.get("extractor_mode"), kwargs.get("conv_bias"))
         layers = self.model.encoder.layers
         if order == "last":                                                 # fe.py:69-71
             self.model.encoder.layers = layers[-num_layers:]
@@ -70,7 +74,7 @@ class XLSR_AASIST(AasistBackend):
 
     def __init__(self, device="cpu", ssl_cpkt_path=None, **kwargs):
         super().__init__()
-        self.ssl_model = self.fe_cls(device, **kwargs) if self.fe_cls is My_XLSR_FE else self.fe_cls(device)
+        self.ssl_model = self.fe_cls(device, **kwargs)
 
     def forward(self, x, taps=None):
         feats = self.ssl_model.extract_feat(x.squeeze(-1))                  # xlsr_aasist.py:88
@@ -113,7 +117,7 @@ class ConformerModel(nn.Module):
     def __init__(self, device="cpu", ssl_cpkt_path=None, **kwargs):
         super().__init__()
         emb = kwargs.get("emb_size", 144)
-        self.ssl_model = self.fe_cls(device, **kwargs) if self.fe_cls is My_XLSR_FE else self.fe_cls(device)
+        self.ssl_model = self.fe_cls(device, **kwargs)
         self.LL = nn.Linear(1024, emb)
         self.first_bn = nn.BatchNorm2d(1)
         self.conformer = MyConformer(emb_size=emb, n_encoders=kwargs.get("n_encoders", 4),

@@ -27,6 +27,14 @@ int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w, const
                        static_cast<bf16*>(out_bf16));
 }
 
+long long rtdf_conv0_gn_workspace_floats(int batch, int n) { return (long long)conv0_gn_workspace_floats(batch, n); }
+
+int rtdf_conv0_gn_gelu(const float* wav, int batch, int n, const float* w, const float* bias, const float* gamma,
+                       const float* beta, float eps, float* workspace, float* out_f32, void* out_bf16, void* stream) {
+  return conv0_gn_gelu(static_cast<cudaStream_t>(stream), wav, batch, n, w, bias, gamma, beta, eps, workspace, out_f32,
+                       static_cast<bf16*>(out_bf16));
+}
+
 int rtdf_layernorm_rows(const void* in, int in_is_bf16, long long rows, int cols, const float* gamma,
                         const float* beta, float eps, int act, float* out_f32, void* out_bf16, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);

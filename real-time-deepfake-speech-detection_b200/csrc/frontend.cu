@@ -213,6 +213,130 @@ int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv-0 in fairseq's extractor_mode="default" (wav2vec2-base style; SURVEY.md App. A.2 step 1, alternative):
+//   conv (bias optional) -> GroupNorm(512 groups, 512 channels) = per-(utterance, channel) normalisation over TIME
+//   -> GELU.  The statistics span the whole utterance, so the layer is two sweeps over the (cheap, K = 10) conv:
+//     1. conv0_gn_stats_kernel     per-CTA partial (sum, sum of squares) of every channel over 256 frames
+//     2. conv0_gn_finalize_kernel  partials added in chunk order in fp64 -> scale = gamma*rstd, shift = beta - mean*scale
+//     3. conv0_gn_apply_kernel     conv recomputed, y = gelu(v*scale + shift), channels-last output
+//   The pre-norm activation (B, L1, 512) fp32 = 1.7 GB at batch 64 never exists in memory.  thread = 2 channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnFrames = 256;                 // frames per CTA
+constexpr int kGnSamples = 5 * kGnFrames + 5;  // samples they read
+
+__device__ __forceinline__ void gn_stage(const float* __restrict__ xb, int N, int t0, float* sx) {
+  for (int i = threadIdx.x; i < kGnSamples; i += 256) {
+    const int j = 5 * t0 + i;
+    sx[i] = j < N ? xb[j] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv0_gn_stats_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
+                      const float* __restrict__ bias, float* __restrict__ partial /*[B][chunks][2][512]*/) {
+  __shared__ float sx[kGnSamples];
+  const int b = blockIdx.y, t0 = blockIdx.x * kGnFrames, c = threadIdx.x * 2;
+  gn_stage(wav + (long long)b * N, N, t0, sx);
+  float w0[10], w1[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) { w0[k] = w_t[k * 512 + c]; w1[k] = w_t[k * 512 + c + 1]; }
+  const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int nf = min(kGnFrames, L1 - t0);
+  for (int f = 0; f < nf; ++f) {
+    float v0 = b0, v1 = b1;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float x = sx[5 * f + k];
+      v0 = fmaf(x, w0[k], v0);
+      v1 = fmaf(x, w1[k], v1);
+    }
+    s0 += v0; s1 += v1;
+    q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
+  }
+  float* p = partial + ((long long)b * gridDim.x + blockIdx.x) * 1024;
+  p[c] = s0; p[c + 1] = s1;
+  p[512 + c] = q0; p[512 + c + 1] = q1;
+}
+
+__global__ void __launch_bounds__(512)
+conv0_gn_finalize_kernel(const float* __restrict__ partial, int chunks, int L1, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, float* __restrict__ scale_shift /*[B][2][512]*/) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < chunks; ++i) {
+    const float* p = partial + ((long long)b * chunks + i) * 1024;
+    s += (double)p[c];
+    q += (double)p[512 + c];
+  }
+  const double mean = s / L1;
+  const double var = fmax(q / L1 - mean * mean, 0.0);
+  const float sc = gamma[c] * (float)(1.0 / sqrt(var + (double)eps));
+  scale_shift[(long long)b * 1024 + c] = sc;
+  scale_shift[(long long)b * 1024 + 512 + c] = beta[c] - (float)mean * sc;
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+conv0_gn_apply_kernel(const float* __restrict__ wav, int N, int L1, const float* __restrict__ w_t,
+                      const float* __restrict__ bias, const float* __restrict__ scale_shift, TOut* __restrict__ out) {
+  __shared__ float sx[kGnSamples];
+  const int b = blockIdx.y, t0 = blockIdx.x * kGnFrames, c = threadIdx.x * 2;
+  gn_stage(wav + (long long)b * N, N, t0, sx);
+  float w0[10], w1[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) { w0[k] = w_t[k * 512 + c]; w1[k] = w_t[k * 512 + c + 1]; }
+  const float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
+  const float* ss = scale_shift + (long long)b * 1024;
+  const float sc0 = ss[c], sc1 = ss[c + 1], sh0 = ss[512 + c], sh1 = ss[512 + c + 1];
+  __syncthreads();
+  const int nf = min(kGnFrames, L1 - t0);
+  TOut* o = out + ((long long)b * L1 + t0) * 512 + c;
+  for (int f = 0; f < nf; ++f) {
+    float v0 = b0, v1 = b1;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float x = sx[5 * f + k];
+      v0 = fmaf(x, w0[k], v0);
+      v1 = fmaf(x, w1[k], v1);
+    }
+    v0 = fmaf(v0, sc0, sh0);
+    v1 = fmaf(v1, sc1, sh1);
+    if (sizeof(TOut) == 2) {
+      const float2 g = gelu2(make_float2(v0, v1));     // fitted GELU: |err| <= 2.6e-5, below the bf16 rounding step
+      *reinterpret_cast<uint32_t*>(o + (long long)f * 512) = pack_bf16x2(g.x, g.y);
+    } else {
+      *reinterpret_cast<float2*>(o + (long long)f * 512) = make_float2(gelu_erf(v0), gelu_erf(v1));
+    }
+  }
+}
+
+size_t conv0_gn_workspace_floats(int B, int N) {
+  const int L1 = N >= 10 ? (N - 10) / 5 + 1 : 0;
+  return (size_t)B * ceil_div(L1, kGnFrames) * 1024 + (size_t)B * 1024;
+}
+
+int conv0_gn_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w_t, const float* bias, const float* gamma,
+                  const float* beta, float eps, float* ws, float* out_f32, bf16* out_bf16) {
+  RTDF_REQUIRE(wav && w_t && gamma && beta && ws && N >= 10 && B > 0 && B <= 65535, "conv0_gn: bad arguments");
+  RTDF_REQUIRE((out_f32 != nullptr) != (out_bf16 != nullptr), "conv0_gn: exactly one output must be given");
+  const int L1 = (N - 10) / 5 + 1;
+  const int chunks = ceil_div(L1, kGnFrames);
+  float* partial = ws;
+  float* scale_shift = ws + (size_t)B * chunks * 1024;
+  dim3 grid(chunks, B);
+  conv0_gn_stats_kernel<<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, partial);
+  RTDF_LAUNCH_CHECK();
+  conv0_gn_finalize_kernel<<<B, 512, 0, s>>>(partial, chunks, L1, gamma, beta, eps, scale_shift);
+  RTDF_LAUNCH_CHECK();
+  if (out_f32) conv0_gn_apply_kernel<float><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, scale_shift, out_f32);
+  else conv0_gn_apply_kernel<bf16><<<grid, 256, 0, s>>>(wav, N, L1, w_t, bias, scale_shift, out_bf16);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row LayerNorm.  Fast path: C % 128 == 0 and C <= 1024, one warp per row, row cached in registers
 // (single global read), two-pass statistics.  Generic path: any C, three strided passes.
 // ------------------------------------------------------------------------------------------------

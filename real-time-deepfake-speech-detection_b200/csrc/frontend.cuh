@@ -15,6 +15,12 @@ int wave_layernorm(cudaStream_t s, const float* x, float* y, int B, int N, float
 int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w_t, const float* bias,
                   const float* gamma, const float* beta, float eps, float* out_f32, bf16* out_bf16);
 
+// conv-0 in extractor_mode="default" (group norm): conv (bias may be NULL) -> GroupNorm(512, 512) over time -> GELU.
+// ws: conv0_gn_workspace_floats(B, N) floats of scratch (per-chunk partial statistics + per-utterance scale / shift).
+size_t conv0_gn_workspace_floats(int B, int N);
+int conv0_gn_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w_t, const float* bias, const float* gamma,
+                  const float* beta, float eps, float* ws, float* out_f32, bf16* out_bf16);
+
 // Row LayerNorm: in (rows, C) fp32 or bf16 -> optional fp32 and/or bf16 outputs, optional activation.
 int layernorm_rows_f32(cudaStream_t s, const float* in, long long rows, int C, const float* gamma, const float* beta,
                        float eps, int act, float* out_f32, bf16* out_bf16);

@@ -129,18 +129,28 @@ static int pack_xlsr(rtdf_ctx* c) {
   const bool bf = c->d.precision == RTDF_PREC_BF16;
   static const int ks[7] = {10, 3, 3, 3, 3, 2, 2};
   static const int ss[7] = {5, 2, 2, 2, 2, 2, 2};
+  // fairseq extractor_mode: "layer_norm" (XLS-R: conv bias + per-frame LayerNorm(512) after every conv, keys
+  // conv_layers.{i}.2.1.*) or "default" (wav2vec2-base style: GroupNorm(512, 512) over time after conv-0 only, keys
+  // conv_layers.0.2.*, usually no conv bias) -- recognised from the state-dict keys.
+  const std::string fe0 = P + "feature_extractor.conv_layers.0";
+  c->fe_group_norm = c->raw.count(fe0 + ".2.1.weight") == 0 && c->raw.count(fe0 + ".2.weight") != 0;
   for (int i = 0; i < 7; ++i) {
     FeConv& f = c->fe[i];
     f.k = ks[i];
     f.stride = ss[i];
     const std::string cp = P + "feature_extractor.conv_layers." + std::to_string(i);
-    if (c->raw.count(cp + ".2.1.weight") == 0) {
-      set_error("rtdf_finalize: '%s.2.1.weight' not found -- only extractor_mode=layer_norm (XLS-R) is implemented; "
-                "group-norm (wav2vec2-base) feature encoders are unsupported", cp.c_str());
-      return RTDF_ERR_UNSUPPORTED;
+    if (c->fe_group_norm) {
+      if (i == 0) RTDF_TRY(make_ln(c, cp + ".2", 512, &f.ln));      // GroupNorm affine (per channel)
+    } else {
+      if (c->raw.count(cp + ".2.1.weight") == 0) {
+        set_error("rtdf_finalize: neither '%s.2.1.weight' (extractor_mode=layer_norm) nor '%s.2.weight' (group norm) found",
+                  cp.c_str(), fe0.c_str());
+        return RTDF_ERR_STATE;
+      }
+      RTDF_TRY(make_ln(c, cp + ".2.1", 512, &f.ln));
     }
-    RTDF_TRY(make_ln(c, cp + ".2.1", 512, &f.ln));
-    RTDF_TRY(get_ptr(c, cp + ".0.bias", &f.lin.b, 512));
+    if (c->raw.count(cp + ".0.bias")) RTDF_TRY(get_ptr(c, cp + ".0.bias", &f.lin.b, 512));   // conv_bias=False: no key
+    else if (!c->fe_group_norm) RTDF_TRY(get_ptr(c, cp + ".0.bias", &f.lin.b, 512));          // reports the missing key
     const int ci = i == 0 ? 1 : 512;
     const float* w;
     RTDF_TRY(get_ptr(c, cp + ".0.weight", &w, 512LL * ci * f.k));
@@ -498,6 +508,7 @@ struct FrontWs {
   float* feats;            // (M,1024) fp32
   int* ln_cnt;             // per 128-row block tile counters of the fused GEMM + LayerNorm (zeroed each forward)
   float* partials;         // [<= 8][M][1024] K-split partial sums of out_proj / fc2 (streaming-chunk regime only)
+  float* gn_ws;            // group-norm extractor mode: conv-0 partial statistics + per-utterance scale / shift
   float* conv_f32;         // (rows, 512) pre-LayerNorm conv output of the short conv layers (streaming-chunk regime only)
   long long conv_f32_rows; // its capacity in rows (0 = not planned)
 };
@@ -516,6 +527,7 @@ static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_
   w->hbuf = b.take<char>((long long)d.M * 4096 * es);
   w->feats = own_feats ? b.take<float>((long long)d.M * 1024) : nullptr;
   w->ln_cnt = b.take<int>(d.M / 128 + 2);
+  w->gn_ws = c->fe_group_norm ? b.take<float>((long long)conv0_gn_workspace_floats(d.B, d.N)) : nullptr;
   w->partials = d.M <= kSkinnyRows ? b.take<float>(8LL * d.M * 1024) : nullptr;
   w->conv_f32_rows = d.M <= kSkinnyRows && (long long)d.B * d.L[1] <= kSmallConvRows ? (long long)d.B * d.L[1] : 0;
   w->conv_f32 = w->conv_f32_rows > 0 ? b.take<float>(w->conv_f32_rows * 512) : nullptr;
@@ -681,15 +693,48 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     RTDF_TRY(preemph(s, wav, w.wav_pe, B, d.N, coef));
     wav = w.wav_pe;
   }
-  // conv-0 (+bias +LN +GELU) -> channels-last (B,L1,512)
-  RTDF_TRY(conv0_ln_gelu(s, wav, B, d.N, c->fe[0].lin.w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f,
-                         bf ? nullptr : static_cast<float*>(w.actA), bf ? static_cast<bf16*>(w.actA) : nullptr));
+  // conv-0 (+bias +LN +GELU | +GroupNorm over time +GELU) -> channels-last (B,L1,512)
+  const bool gn = c->fe_group_norm;
+  if (gn)
+    RTDF_TRY(conv0_gn_gelu(s, wav, B, d.N, c->fe[0].lin.w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f, w.gn_ws,
+                           bf ? nullptr : static_cast<float*>(w.actA), bf ? static_cast<bf16*>(w.actA) : nullptr));
+  else
+    RTDF_TRY(conv0_ln_gelu(s, wav, B, d.N, c->fe[0].lin.w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f,
+                           bf ? nullptr : static_cast<float*>(w.actA), bf ? static_cast<bf16*>(w.actA) : nullptr));
   void* cur = w.actA;
   void* nxt = w.actB;
   for (int i = 1; i < 7; ++i) {
     const FeConv& f = c->fe[i];
     const int Lin_ = d.L[i - 1], Lout = d.L[i];
-    if (bf && w.conv_f32 && (long long)B * Lout <= w.conv_f32_rows && skinny_rows(c, M)) {
+    if (gn) {
+      // extractor_mode="default": conv (no LayerNorm) -> GELU, as an implicit GEMM with the activation in the epilogue
+      TcEpilogue e;
+      e.bias = f.lin.b;
+      e.act = ACT_GELU;
+      if (bf) {
+        TcOperandA a;
+        a.ptr = static_cast<const bf16*>(cur);
+        a.k_extent = (long long)f.k * 512;
+        a.rows_per_batch = Lout;
+        a.batches = B;
+        a.row_stride = (long long)f.stride * 512;
+        a.batch_stride = (long long)Lin_ * 512;
+        e.out_bf16 = static_cast<bf16*>(nxt);
+        e.ld_bf16 = 512;
+        RTDF_TRY(tc_gemm(s, a, f.lin.wb, 512, f.k * 512, TC_PLAIN, 256, e));
+      } else {
+        SimtOperandA a;
+        a.ptr = static_cast<const float*>(cur);
+        a.k_extent = (long long)f.k * 512;
+        a.rows_per_batch = Lout;
+        a.batches = B;
+        a.row_stride = (long long)f.stride * 512;
+        a.batch_stride = (long long)Lin_ * 512;
+        e.out_f32 = static_cast<float*>(nxt);
+        e.ld_f32 = 512;
+        RTDF_TRY(simt_gemm_f32(s, a, f.lin.w, 512, f.k * 512, e));
+      }
+    } else if (bf && w.conv_f32 && (long long)B * Lout <= w.conv_f32_rows && skinny_rows(c, M)) {
       // Streaming chunks: a full-row (N = 512) tile leaves one CTA per 128 output rows, each streaming the whole weight
       // matrix.  64-wide tiles give 8x the CTAs; bias goes in the GEMM, LayerNorm + GELU in a row kernel (fp32 in between).
       TcOperandA a;

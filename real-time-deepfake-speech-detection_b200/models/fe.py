@@ -13,26 +13,38 @@ from torch import nn
 
 from ._rt import engine_for
 from .aasist_modules import *  # noqa: F401,F403  (reference fe.py:1)
-from .wav2vec2_params import Wav2Vec2Model, load_pretrained
+from .wav2vec2_params import Wav2Vec2Model, extractor_config, read_checkpoint
 
 __all__ = ["XLSR_FE", "My_XLSR_FE", "middle_indices"] + [
     "GraphAttentionLayer", "HtrgGraphAttentionLayer", "GraphPool", "Residual_block"]
 
 
-def _build_ssl(device):
-    model = Wav2Vec2Model()
+def _build_ssl(device, extractor_mode=None, conv_bias=None):
+    """The SSL model the reference gets from fairseq (fe.py:11-15).  With $RTDF_XLSR_CKPT the conv feature encoder's
+    mode (per-frame LayerNorm + conv bias for XLS-R, GroupNorm after conv-0 for wav2vec2-base style checkpoints) follows
+    the checkpoint; without it, ``extractor_mode`` / $RTDF_XLSR_EXTRACTOR_MODE (default "layer_norm") picks the layout of
+    the randomly initialised model."""
     path = os.environ.get("RTDF_XLSR_CKPT")
-    if path:
-        load_pretrained(model, path)
+    sd = read_checkpoint(path) if path else None
+    if sd is not None:
+        extractor_mode, conv_bias = extractor_config(sd)
+    extractor_mode = extractor_mode or os.environ.get("RTDF_XLSR_EXTRACTOR_MODE", "layer_norm")
+    if conv_bias is None:
+        conv_bias = extractor_mode == "layer_norm"
+    model = Wav2Vec2Model(extractor_mode=extractor_mode, conv_bias=conv_bias)
+    if sd is not None:
+        missing, _ = model.load_state_dict(sd, strict=False)
+        if missing:
+            raise RuntimeError(f"checkpoint {path} lacks XLS-R keys, e.g. {missing[:3]}")
     return model.to(device)
 
 
 class XLSR_FE(nn.Module):
     """reference models/fe.py:8-40."""
 
-    def __init__(self, device):
+    def __init__(self, device, extractor_mode=None, conv_bias=None):
         super().__init__()
-        self.model = _build_ssl(device)
+        self.model = _build_ssl(device, extractor_mode, conv_bias)
         self.out_dim = 1024
 
     def extract_feat(self, input_data):
@@ -69,7 +81,7 @@ class My_XLSR_FE(XLSR_FE):
         custom_order = kwargs.get('custom_order', None)
         if num_layers < 1 or num_layers > 24:
             raise ValueError("Number of layers must be at least 1 and at most 24.")
-        super().__init__(device)
+        super().__init__(device, kwargs.get('extractor_mode'), kwargs.get('conv_bias'))
         self.num_layers, self.order, self.custom_order = num_layers, order, custom_order
         layers = self.model.encoder.layers
         if order == 'last':

@@ -56,16 +56,28 @@ class TransformerSentenceEncoderLayer(_Container):
 
 
 class _FeatureExtractor(_Container):
-    def __init__(self):
+    """fairseq ``ConvFeatureExtractionModel`` parameter layout.  mode "layer_norm" (XLS-R): conv bias and a LayerNorm(512)
+    after every conv (keys ``conv_layers.{i}.2.1.*``); mode "default" (wav2vec2-base style): GroupNorm(512, 512) after
+    conv-0 only (keys ``conv_layers.0.2.*``), ``conv_bias`` normally False."""
+
+    def __init__(self, mode="layer_norm", conv_bias=True):
         super().__init__()
+        if mode not in ("layer_norm", "default"):
+            raise ValueError(f"extractor_mode must be 'layer_norm' or 'default', got {mode!r}")
         self.conv_layers = nn.ModuleList()
         in_d = 1
-        for dim, k, s in CONV_LAYERS:
-            conv = nn.Conv1d(in_d, dim, k, stride=s, bias=True)
+        for i, (dim, k, s) in enumerate(CONV_LAYERS):
+            conv = nn.Conv1d(in_d, dim, k, stride=s, bias=conv_bias)
             nn.init.kaiming_normal_(conv.weight)
-            # index 0: conv, 1: dropout, 2: (transpose, LayerNorm, transpose), 3: GELU  (fairseq layout)
-            self.conv_layers.append(nn.Sequential(
-                conv, nn.Identity(), nn.Sequential(nn.Identity(), nn.LayerNorm(dim), nn.Identity()), nn.Identity()))
+            # index 0: conv, 1: dropout, 2: norm, 3: GELU  (fairseq layout)
+            if mode == "layer_norm":      # 2: (transpose, LayerNorm, transpose)
+                block = nn.Sequential(conv, nn.Identity(), nn.Sequential(nn.Identity(), nn.LayerNorm(dim), nn.Identity()),
+                                      nn.Identity())
+            elif i == 0:                  # 2: GroupNorm(dim, dim)
+                block = nn.Sequential(conv, nn.Identity(), nn.GroupNorm(dim, dim), nn.Identity())
+            else:                         # conv, dropout, GELU
+                block = nn.Sequential(conv, nn.Identity(), nn.Identity())
+            self.conv_layers.append(block)
             in_d = dim
 
 
@@ -78,9 +90,9 @@ class _Encoder(_Container):
 
 
 class Wav2Vec2Model(_Container):
-    def __init__(self, dim=1024, ffn=4096, layers=24):
+    def __init__(self, dim=1024, ffn=4096, layers=24, extractor_mode="layer_norm", conv_bias=True):
         super().__init__()
-        self.feature_extractor = _FeatureExtractor()
+        self.feature_extractor = _FeatureExtractor(extractor_mode, conv_bias)
         self.layer_norm = nn.LayerNorm(512)
         self.post_extract_proj = nn.Linear(512, dim)
         self.mask_emb = nn.Parameter(torch.empty(dim).uniform_())
@@ -98,11 +110,23 @@ class Wav2Vec2Model(_Container):
             del state_dict[k]
 
 
-def load_pretrained(model, path):
-    """Load a fairseq XLS-R checkpoint (``{'model': state_dict, ...}``) or a plain state dict."""
+def read_checkpoint(path):
+    """State dict of a fairseq checkpoint (``{'model': state_dict, ...}``) or of a plain state-dict file, without the
+    pre-training heads."""
     ckpt = torch.load(path, map_location="cpu", weights_only=False)
     sd = ckpt.get("model", ckpt) if isinstance(ckpt, dict) else ckpt
-    sd = {k: v for k, v in sd.items() if not k.startswith(_IGNORED_PREFIXES)}
+    return {k: v for k, v in sd.items() if not k.startswith(_IGNORED_PREFIXES)}
+
+
+def extractor_config(sd):
+    """(extractor_mode, conv_bias) a checkpoint was trained with, read off its keys."""
+    mode = "layer_norm" if "feature_extractor.conv_layers.0.2.1.weight" in sd else "default"
+    return mode, "feature_extractor.conv_layers.0.0.bias" in sd
+
+
+def load_pretrained(model, path):
+    """Load a fairseq XLS-R checkpoint (``{'model': state_dict, ...}``) or a plain state dict."""
+    sd = read_checkpoint(path)
     missing, unexpected = model.load_state_dict(sd, strict=False)
     if missing:
         raise RuntimeError(f"checkpoint {path} lacks XLS-R keys, e.g. {missing[:3]}")

@@ -82,7 +82,7 @@ class XLSR_AASIST(_AasistBase):
 
     def __init__(self, device, ssl_cpkt_path=None, **kwargs) -> None:
         super().__init__()
-        self.ssl_model = XLSR_FE(device)
+        self.ssl_model = XLSR_FE(device, kwargs.get('extractor_mode'), kwargs.get('conv_bias'))
         self._apply_freeze_kwargs(kwargs)
         self._build_backend()
 

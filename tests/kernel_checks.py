@@ -109,6 +109,37 @@ def check_conv0():
     return out
 
 
+def check_conv0_groupnorm():
+    """conv-0 of the group-norm feature encoder (fairseq extractor_mode="default"): conv -> GroupNorm(512, 512) over
+    time -> GELU, with and without a conv bias, ragged chunk boundaries (L1 = 3199, 799, 256, 257)."""
+    from tests.util import native
+    lib = native().load()
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    for B, N, with_bias in ((2, 16000, False), (3, 4003, True), (1, 1285, False), (2, 1290, True)):
+        wav = torch.randn(B, N, generator=g) * 0.1 + 0.02
+        w = torch.randn(512, 1, 10, generator=g) * 0.4
+        b = torch.randn(512, generator=g) * 0.1 if with_bias else None
+        gamma = 1 + 0.1 * torch.randn(512, generator=g)
+        beta = 0.1 * torch.randn(512, generator=g)
+        y = F.conv1d(wav.unsqueeze(1), w, b, stride=5)                              # (B,512,L)
+        ref = F.gelu(F.group_norm(y, 512, gamma, beta, 1e-5)).transpose(1, 2)       # (B,L,512)
+        L = ref.shape[1]
+        ws = torch.empty(int(lib.rtdf_conv0_gn_workspace_floats(B, N)), device=DEV)
+        wt = w[:, 0, :].t().contiguous().to(DEV)
+        o32 = torch.full((B, L, 512), float("nan"), device=DEV)
+        o16 = torch.zeros(B, L, 512, dtype=torch.bfloat16, device=DEV)
+        bd = dev(b) if with_bias else None
+        call("rtdf_conv0_gn_gelu", P(dev(wav)), B, N, P(wt), P(bd), P(dev(gamma)), P(dev(beta)), 1e-5, P(ws), P(o32), None, stream())
+        call("rtdf_conv0_gn_gelu", P(dev(wav)), B, N, P(wt), P(bd), P(dev(gamma)), P(dev(beta)), 1e-5, P(ws), None, P(o16), stream())
+        d32 = float((o32.cpu() - ref).abs().max())
+        d16 = float((o16.float().cpu() - ref).abs().max())
+        out[f"{B}x{N}_bias{int(with_bias)}"] = (d32, d16)
+        assert d32 <= 5e-5, out
+        assert d16 <= 0.03, out
+    return out
+
+
 def check_gemm_f32():
     g = torch.Generator().manual_seed(2)
     out = {}

@@ -40,6 +40,10 @@ def test_e2e_student_conformer_fixed_call():
     ("conformer_n64600_b1", "bf16"),
     ("conformer_n16000_b2", "fp32"),
     ("student2_conformer_n16000_b2", "bf16"),
+    # fairseq extractor_mode="default": GroupNorm over time after conv-0, plain conv + GELU after (no conv bias)
+    ("student2_aasist_groupnorm_n16000_b2", "fp32"),
+    ("student2_aasist_groupnorm_n16000_b2", "bf16"),
+    ("student2_aasist_groupnorm_n64600_b1", "bf16"),
 ])
 def test_golden_vectors_from_reference(name, precision):
     ec.check_golden(name, precision=precision)

@@ -28,6 +28,10 @@ def test_conv0_ln_gelu():
     kc.check_conv0()
 
 
+def test_conv0_groupnorm_gelu():
+    kc.check_conv0_groupnorm()
+
+
 def test_gemm_f32():
     kc.check_gemm_f32()
 

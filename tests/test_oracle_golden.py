@@ -11,7 +11,8 @@ from tests.util import ROOT
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-@pytest.mark.parametrize("name", ["xlsr_aasist_n16000_b2", "student_mid4_aasist_n16000_b2", "conformer_n16000_b2"])
+@pytest.mark.parametrize("name", ["xlsr_aasist_n16000_b2", "student_mid4_aasist_n16000_b2", "conformer_n16000_b2",
+                                  "student2_aasist_groupnorm_n16000_b2"])
 def test_oracle_matches_reference_golden(name):
     from oracle import models_ref as O
     g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)

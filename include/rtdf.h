@@ -161,7 +161,8 @@ int rtdf_posconv_bf16(float* x_f32, const void* x_bf16, int batch, int n_frames,
 int rtdf_posconv_f32(float* x, const float* x_in, int batch, int n_frames, const float* w_packed, const float* bias,
                      void* stream);
 /* qkv (B*T, 3*H*64) [q|k|v] with q pre-scaled -> ctx (B*T, H*64).  impl 0 = tcgen05 warp-specialised (P in
- * tensor memory), 1 = SIMT, 2 = tcgen05 one-tile-per-CTA kernel. */
+ * tensor memory; T <= 512 frames: two ping-pong TMEM buffers up to 256 frames, one 512-column buffer above),
+ * 1 = SIMT (any T that fits shared memory), 2 = tcgen05 one-tile-per-CTA kernel (T <= 256). */
 int rtdf_attention(const void* qkv, void* ctx_out, int batch, int n_frames, int heads, int is_bf16, int impl,
                    void* stream);
 /* Weights of one graph-attention row pass (device pointers).  *_t matrices are transposed to [D][DO]; bn_s / bn_t are the

@@ -184,6 +184,11 @@ constexpr int kWsMaxStages = 6;
 
 struct AttWsParams {
   int T, H, Tk, n_qt, total_items, n_stages, stage_bytes, kv_bytes;
+  // T <= 256: two TMEM buffers of 256 columns (ping-pong), K / V in one TMA box each, O at column 128.
+  // 256 < T <= 512 (5.1 .. 10.2 s of audio): S of one query tile fills all 512 columns, so there is ONE buffer, one
+  // softmax warpgroup works, K / V arrive as two 256-row boxes (rows past T zero-filled by TMA), S = two N <= 256 MMAs
+  // per k-step, O sits at column 448 (S columns consumed before P V is issued; P covers [0, Tk/2 <= 256)).
+  int n_buf, buf_cols, o_col, kv_boxes;
   // RTDF_ATTN_DEBUG bit mask -- timing experiments only, the output is wrong when any bit is set (tools/attention_experiment.py):
   // 1 = no row-max pass, 2 = exp pass on the first chunk only, 4 = no TMA loads, 8 = no S MMAs, 16 = no PV MMAs, 32 = no O store
   int debug;
@@ -250,41 +255,51 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         mbar_expect_tx(full_bar(s), 16384u + 2u * p.kv_bytes);
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384, sV = sK + p.kv_bytes;
         tma_load_3d(sQ, &mapQ, full_bar(s), h * 64, qt * 128, b);
-        tma_load_3d(sK, &mapKV, full_bar(s), HD + h * 64, 0, b);
-        tma_load_3d(sV, &mapKV, full_bar(s), 2 * HD + h * 64, 0, b);
+        for (int bx = 0; bx < p.kv_boxes; ++bx) {
+          tma_load_3d(sK + bx * 32768, &mapKV, full_bar(s), HD + h * 64, bx * 256, b);
+          tma_load_3d(sV + bx * 32768, &mapKV, full_bar(s), 2 * HD + h * 64, bx * 256, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc_s = umma_idesc_bf16(128, p.Tk);
+      const int n1 = p.Tk < 256 ? p.Tk : 256, n2 = p.Tk - n1;      // S columns [0, n1) and [256, 256 + n2)
+      const uint32_t idesc_s = umma_idesc_bf16(128, n1);
+      const uint32_t idesc_s2 = n2 > 0 ? umma_idesc_bf16(128, n2) : 0u;
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, /*a_mn=*/0, /*b_mn=*/1);
       const int ksteps = p.Tk / 16;
+      const int nb = p.n_buf;
       auto issue_pv = [&](int j) {
-        const int g = j & 1, s = j % p.n_stages;
-        mbar_wait(pfull_bar(g), (j >> 1) & 1);
+        const int g = j % nb, s = j % p.n_stages;
+        mbar_wait(pfull_bar(g), (j / nb) & 1);
         tc_fence_after();
         const uint32_t sV = base + s * p.stage_bytes + 16384 + p.kv_bytes;
-        const uint32_t tP = tmem + g * 256, tO = tmem + g * 256 + 128;
+        const uint32_t tP = tmem + g * p.buf_cols, tO = tP + p.o_col;
         for (int ks = 0; ks < ksteps && !(p.debug & 16); ++ks)
           mma_bf16_ts(tO, tP + ks * 8, umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
         mma_commit(empty_bar(s));     // Q, K, V of this stage are no longer read
         mma_commit(ofull_bar(g));
       };
       for (int i = 0; i < n_local; ++i) {
-        const int g = i & 1, s = i % p.n_stages;
-        mbar_wait(tempty_bar(g), ((i >> 1) & 1) ^ 1);   // warpgroup g has read O of item i - 2
+        const int g = i % nb, s = i % p.n_stages;
+        mbar_wait(tempty_bar(g), ((i / nb) & 1) ^ 1);   // warpgroup g has read O of item i - n_buf
         mbar_wait(full_bar(s), (i / p.n_stages) & 1);
         tc_fence_after();
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (!(p.debug & 8))
-            mma_bf16_ss(tmem + g * 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+          if (!(p.debug & 8)) {
+            mma_bf16_ss(tmem + g * p.buf_cols, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+            if (n2 > 0)
+              mma_bf16_ss(tmem + g * p.buf_cols + 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + 32768 + k * 32),
+                          idesc_s2, k != 0);
+          }
         mma_commit(sfull_bar(g));
-        if (i > 0) issue_pv(i - 1);
+        if (nb == 1) issue_pv(i);          // single buffer: S(i+1) has to wait for O(i) anyway
+        else if (i > 0) issue_pv(i - 1);   // ping-pong: S(i) is issued ahead of P V(i-1)
       }
-      if (n_local > 0) issue_pv(n_local - 1);
+      if (nb == 2 && n_local > 0) issue_pv(n_local - 1);
       pdl_launch_dependents();
     }
   } else {
@@ -292,14 +307,14 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;                      // TMEM lane quarter of this warp
     const int r = q * 32 + lane;                 // row inside the query tile
-    const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
-    const int nchunks = p.Tk / 16;
+    const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + g * p.buf_cols;
     const int T = p.T;
+    const int nb = p.n_buf;
     const float kLog2e = 1.4426950408889634f;
-    for (int i = g; i < n_local; i += 2) {
+    for (int i = g; i < n_local && g < nb; i += nb) {
       const int item = blockIdx.x + i * gridDim.x;
       const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
-      const uint32_t ph = (i >> 1) & 1;
+      const uint32_t ph = (i / nb) & 1;
       const bool warp_active = qt * 128 + q * 32 < T;        // warp-uniform: any valid query row in this warp
       mbar_wait(sfull_bar(g), ph);
       __syncwarp();
@@ -381,8 +396,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const float inv = 1.0f / sum;
         const int tq = qt * 128 + r;
         uint32_t v0[32], v1[32];
-        tmem_ld32(t_row + 128, v0);
-        tmem_ld32(t_row + 160, v1);
+        tmem_ld32(t_row + p.o_col, v0);
+        tmem_ld32(t_row + p.o_col + 32, v1);
         tmem_ld_wait();
         if (tq < T) {
           bf16* dst = ctx + ((long long)b * T + tq) * HD + h * 64;
@@ -417,7 +432,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 
 int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H) {
   RTDF_REQUIRE(qkv && ctx && B > 0 && H > 0, "attention_ws: bad arguments");
-  RTDF_REQUIRE(T >= 1 && T <= 256, "attention_ws: T = %d frames unsupported (1..256; <= 5.1 s of audio)", T);
+  RTDF_REQUIRE(T >= 1 && T <= 512, "attention_ws: T = %d frames unsupported (1..512; <= 10.2 s of audio)", T);
   AttWsParams p;
   {
     static int dbg = -1;
@@ -434,18 +449,23 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   const long long items = (long long)B * H * p.n_qt;
   RTDF_REQUIRE(items < (1LL << 30), "attention_ws: batch too large");
   p.total_items = (int)items;
-  p.kv_bytes = p.Tk * 128;
+  const bool long_mode = T > 256;
+  p.n_buf = long_mode ? 1 : 2;
+  p.buf_cols = long_mode ? 512 : 256;
+  p.o_col = long_mode ? 448 : 128;
+  p.kv_boxes = long_mode ? 2 : 1;
+  p.kv_bytes = long_mode ? 65536 : p.Tk * 128;
   p.stage_bytes = 16384 + 2 * p.kv_bytes;
   const int budget = 232448 - 1024 - 256;
   p.n_stages = budget / p.stage_bytes;
   if (p.n_stages > kWsMaxStages) p.n_stages = kWsMaxStages;
-  RTDF_REQUIRE(p.n_stages >= 2, "attention_ws: stage of %d bytes does not fit twice", p.stage_bytes);
+  RTDF_REQUIRE(p.n_stages >= (long_mode ? 1 : 2), "attention_ws: stage of %d bytes does not fit", p.stage_bytes);
   const size_t smem = (size_t)p.n_stages * p.stage_bytes + 256 + 1024;
   CUtensorMap mapQ, mapKV;
   uint64_t dims[3] = {(uint64_t)3 * H * 64, (uint64_t)T, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)3 * H * 64 * 2, (uint64_t)T * 3 * H * 64 * 2};
   uint32_t boxq[3] = {64, 128, 1};
-  uint32_t boxkv[3] = {64, (uint32_t)p.Tk, 1};
+  uint32_t boxkv[3] = {64, (uint32_t)(long_mode ? 256 : p.Tk), 1};
   RTDF_TRY(make_tmap_bf16(&mapQ, qkv, 3, dims, strides, boxq, TMAP_SW128));
   RTDF_TRY(make_tmap_bf16(&mapKV, qkv, 3, dims, strides, boxkv, TMAP_SW128));
   RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_ws_kernel), (size_t)smem));

@@ -1,4 +1,4 @@
-// Multi-head self-attention cores for the XLS-R transformer (16 heads x 64, T <= 256 frames).
+// Multi-head self-attention cores for the XLS-R transformer (16 heads x 64; tcgen05 kernel: T <= 512 frames).
 #pragma once
 #include "common.cuh"
 
@@ -9,7 +9,8 @@ namespace rtdf {
 // (bmm -> softmax -> bmm), reference models/fe.py:19.
 
 // tcgen05 path (default): persistent warp-specialised kernel -- TMA producer warp, MMA issuer warp, two softmax
-// warpgroups ping-ponging over two TMEM buffers; S = Q K^T (SS), P written back to TMEM, O = P V (TS).
+// warpgroups ping-ponging over two TMEM buffers; S = Q K^T (SS), P written back to TMEM, O = P V (TS).  T <= 256 frames
+// use two 256-column buffers; 256 < T <= 512 one 512-column buffer (single softmax warpgroup, K / V in two TMA boxes).
 int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H);
 
 // earlier tile kernel, kept for A/B runs: one CTA per (query tile of 128, head, utterance): S = Q K^T in TMEM, fp32 softmax in

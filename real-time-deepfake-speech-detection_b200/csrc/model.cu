@@ -874,7 +874,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       RTDF_TRY(linear(c, s, w.xb, M, L.qkv, e));
     }
     if (bf) {
-      if (T > 256)   // beyond the tcgen05 kernels' single key tile (5.1 s of audio): SIMT kernel, K / V of a head in smem
+      if (T > 512)   // beyond the tcgen05 kernel's 512 key columns of tensor memory (10.2 s of audio): SIMT kernel
         RTDF_TRY(attention_simt_bf16(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
       else if (c->d.attention_impl == 0)
         RTDF_TRY(attention_ws(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));

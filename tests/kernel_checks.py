@@ -455,6 +455,9 @@ ATTN_SHAPES = ((2, 199, 16), (1, 49, 16), (2, 201, 4), (1, 128, 2), (1, 256, 2),
 # the timed configuration (BASELINE configs[2]): 2,048 (utterance, head, query tile) items on <= 148 persistent CTAs, so
 # every CTA loops ~14 times over its smem ring / TMEM buffers / mbarrier phases
 ATTN_SHAPES_TIMED = ((64, 199, 16), (64, 201, 16))
+# 256 < T <= 512 frames (5.1 .. 10.2 s): single 512-column TMEM buffer, K / V in two TMA boxes, S as two MMAs per k-step;
+# (40, 300, 16) gives 1,920 items on 148 CTAs (barrier phases of the one-stage ring flip many times)
+ATTN_SHAPES_LONG = ((1, 257, 2), (2, 300, 4), (1, 400, 16), (1, 512, 2), (2, 272, 1), (40, 300, 16))
 
 
 def check_attention(impls=(0, 1), shapes=ATTN_SHAPES):

@@ -73,6 +73,10 @@ def test_attention(impl):
     kc.check_attention(impls=(impl,))
 
 
+def test_attention_long_utterances_on_tcgen05():
+    kc.check_attention(impls=(0,), shapes=kc.ATTN_SHAPES_LONG)
+
+
 def test_graph_pool_bit_exact_topk():
     kc.check_graph_pool()
 

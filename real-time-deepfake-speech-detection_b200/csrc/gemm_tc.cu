@@ -37,6 +37,9 @@ struct TcKernelParams {
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
   int epi_mode;
   int debug = 0;           // RTDF_GEMM_DEBUG bit mask (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
+  int stream_mode = 0;     // streaming-chunk launches under programmatic dependent launch: dependents are released at the
+                           // start, and the weight (W) tiles of the first ring round are requested BEFORE waiting for the
+                           // previous kernel (they do not depend on it), so the weight stream of kernel k+1 overlaps kernel k
   int k_splits = 1;        // split-K: tile t covers k-blocks [split * kb_per_split, ...) and reduce-adds its partial
   int kb_per_split = 0;
   TcEpilogue epi;
@@ -71,6 +74,18 @@ int tc_profile_end(int variant, double* ms_total, double* flops_total, int* laun
   if (flops_total) *flops_total = fl;
   if (launches) *launches = n;
   return RTDF_OK;
+}
+
+static bool stream_prefetch_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // opt-in experiment (r02): release the dependents at kernel start and request the first ring round of weight tiles
+    // before waiting for the previous kernel.  Measured SLOWER for streaming chunks (batch 1, 1 s: p50 1.44 vs 1.37 ms,
+    // profiles/r02_stream_prefetch_ab.txt): the early dependents only find room on the SMs the running GEMM left idle.
+    const char* e = getenv("RTDF_STREAM_PREFETCH");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 constexpr int BM = 128;
@@ -371,13 +386,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();                // the previous kernel's output (our A operand / residual) is complete and visible
+  const bool stream_mode = p.stream_mode != 0;
+  if (!stream_mode) pdl_wait();   // the previous kernel's output (our A operand / residual) is complete and visible
   const uint32_t tmem_base = *tmem_ptr_gen;
   const int tiles_n = p.tiles_n, tiles_m = p.tiles_m;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      uint32_t pre = 0;
+      if (stream_mode) {
+        // Weight tiles of the first ring round: requested before the wait on the previous kernel.  The stage barrier
+        // expects the bytes of both operands; the A tile follows after the wait.
+        for (int t = blockIdx.x; t < p.total_tiles && pre < (uint32_t)kStages; t += gridDim.x) {
+          const int split = t % p.k_splits, tt = t / p.k_splits;
+          const int n0 = (tt % tiles_n) * BN;
+          const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+          for (int kb = kb0; kb < kb1 && pre < (uint32_t)kStages; ++kb, ++pre) {
+            mbar_expect_tx(full_bar(pre), Cfg::kStageBytes);
+            const uint32_t b_dst = smem_base + pre * Cfg::kStageBytes + Cfg::kABytes;
+#pragma unroll
+            for (int h = 0; h < (BN + 255) / 256; ++h)
+              tma_load_2d(b_dst + h * 256 * BK * 2, &mapB, full_bar(pre), kb * BK, n0 + h * 256);
+          }
+        }
+        pdl_wait();
+      }
       uint32_t it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int split = t % p.k_splits, tt = t / p.k_splits;
@@ -388,19 +422,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
           const uint32_t b_dst = a_dst + Cfg::kABytes;
+          if (it >= pre) {
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          }
           tma_load_3d(a_dst, &mapA, full_bar(s), a_col0 + kb * p.a_kb_col_step,
                       m0 + p.a_row_off + kb * p.a_kb_row_step, batch);
+          if (it >= pre) {
 #pragma unroll
-          for (int h = 0; h < (BN + 255) / 256; ++h)
-            tma_load_2d(b_dst + h * 256 * BK * 2, &mapB, full_bar(s), kb * BK, n0 + h * 256);
+            for (int h = 0; h < (BN + 255) / 256; ++h)
+              tma_load_2d(b_dst + h * 256 * BK * 2, &mapB, full_bar(s), kb * BK, n0 + h * 256);
+          }
         }
       }
     }
   } else if (warp == 1) {
+    if (lane == 0 && stream_mode) pdl_launch_dependents();   // dependents wait for our completion at their pdl_wait()
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr int kInstrN = BN > 256 ? 256 : BN;
@@ -433,10 +472,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mma_commit(tfull_bar(a));    // accumulator stage complete
       }
-      pdl_launch_dependents();       // all MMAs of this CTA are issued: the next kernel may start its prologue
+      if (!stream_mode) pdl_launch_dependents();   // all MMAs of this CTA are issued: the next kernel may start its prologue
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    if (stream_mode) pdl_wait();      // residual reads / output writes follow the previous kernel
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;  // 0 .. kEpiThreads-1
@@ -1304,6 +1344,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   p.epi = epi;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
+  p.stream_mode = (pdl_enabled() && !epi.rowln_counters && stream_prefetch_enabled()) ? 1 : 0;
   p.k_splits = 1;
   p.kb_per_split = p.num_kb;
   if (epi.partials) {

@@ -467,11 +467,12 @@ def check_attention(impls=(0, 1), shapes=ATTN_SHAPES):
         qkv = torch.randn(B * T, 3 * H * 64, generator=g)
         qkv[:, : H * 64] *= 0.25
         ref32 = _attn_ref(qkv, B, T, H)
-        o = torch.empty(B * T, H * 64, dtype=torch.float32, device=DEV)
-        call("rtdf_attention", P(dev(qkv)), P(o), B, T, H, 0, 1, stream())
-        d = float((o.cpu() - ref32).abs().max())
-        out[f"B{B}_T{T}_H{H}_f32"] = d
-        assert d <= 2e-5, out
+        if T <= 400:      # the fp32 SIMT kernel keeps K / V of a head in shared memory
+            o = torch.empty(B * T, H * 64, dtype=torch.float32, device=DEV)
+            call("rtdf_attention", P(dev(qkv)), P(o), B, T, H, 0, 1, stream())
+            d = float((o.cpu() - ref32).abs().max())
+            out[f"B{B}_T{T}_H{H}_f32"] = d
+            assert d <= 2e-5, out
         qb = qkv.to(torch.bfloat16)
         ref16 = _attn_ref(qb, B, T, H)
         for impl in impls:

@@ -290,7 +290,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL may print its version banner on stdout when the first communicator is created: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.all_reduce(torch.zeros(1, device=device))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     xa = importlib.import_module(PKG + ".models.xlsr_aasist")
     native = importlib.import_module(PKG + ".rtdf_runtime.native")

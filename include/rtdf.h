@@ -111,6 +111,13 @@ int rtdf_wave_layernorm(const float* x, float* y, int batch, int n, float eps, v
 int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w_tapmajor /*[10][512]*/, const float* bias,
                        const float* gamma, const float* beta, float eps, float* out_f32 /*or NULL*/,
                        void* out_bf16 /*or NULL*/, void* stream);
+/* The same layer on the tensor cores (what the forward uses for large batches in bf16 mode): conv-0 lowered to an
+ * implicit GEMM with K = 10 taps padded to 32, waveform and weights split into bf16 (hi, lo) pairs laid side by side along
+ * K (three of the four partial products, ~2^-16 relative), bias + LayerNorm(512) + GELU in the tcgen05 tile's epilogue.
+ * w: state-dict layout [512][1][10] fp32.  scratch: rtdf_conv0_tc_scratch_bytes(batch, n) bytes, 128-byte aligned. */
+long long rtdf_conv0_tc_scratch_bytes(int batch, int n);
+int rtdf_conv0_tc_ln_gelu(const float* wav, int batch, int n, const float* w, const float* bias, const float* gamma,
+                          const float* beta, float eps, void* scratch, void* out_bf16, void* stream);
 /* conv-0 of the feature encoder in fairseq's extractor_mode="default" (wav2vec2-base style; the alternative SURVEY.md
  * App. A.2 step 1 describes): Conv1d(1, 512, 10, stride 5, bias optional -- NULL when conv_bias=False) ->
  * GroupNorm(512 groups, 512 channels), i.e. per-(utterance, channel) statistics over time -> GELU; channels-last output

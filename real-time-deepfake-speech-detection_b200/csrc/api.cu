@@ -27,6 +27,21 @@ int rtdf_conv0_ln_gelu(const float* wav, int batch, int n, const float* w, const
                        static_cast<bf16*>(out_bf16));
 }
 
+long long rtdf_conv0_tc_scratch_bytes(int batch, int n) {
+  const long long l1 = n >= 10 ? (n - 10) / 5 + 1 : 0;
+  return ((long long)batch * l1 * 32 + 512 * 32) * 2 + 256;
+}
+
+int rtdf_conv0_tc_ln_gelu(const float* wav, int batch, int n, const float* w, const float* bias, const float* gamma,
+                          const float* beta, float eps, void* scratch, void* out_bf16, void* stream) {
+  RTDF_REQUIRE(w && scratch && (reinterpret_cast<uintptr_t>(scratch) & 127) == 0, "rtdf_conv0_tc_ln_gelu: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bf16* wp = static_cast<bf16*>(scratch);                 // [512][32] packed weight, then the im2col matrix
+  bf16* a = wp + 512 * 32;
+  RTDF_TRY(conv0_tc_pack_weight(s, w, wp));
+  return conv0_tc_ln_gelu(s, wav, batch, n, wp, bias, gamma, beta, eps, a, static_cast<bf16*>(out_bf16));
+}
+
 long long rtdf_conv0_gn_workspace_floats(int batch, int n) { return (long long)conv0_gn_workspace_floats(batch, n); }
 
 int rtdf_conv0_gn_gelu(const float* wav, int batch, int n, const float* w, const float* bias, const float* gamma,

@@ -213,6 +213,83 @@ int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv-0 on the tensor cores (large batches): the layer as the implicit GEMM  out[m][n] = sum_k A[m][k] W[n][k],
+// m = (utterance, frame), k = tap, n = channel, with K = 10 padded to 32 and both operands split into bf16 (hi, lo)
+// pairs laid side by side along K so that ONE bf16 GEMM carries three of the four partial products (~2^-16 relative,
+// the raw waveform is never rounded to 8 mantissa bits):
+//     A row = [ hi(x_0..x_9) | lo(x_0..x_9) | hi(x_0..x_9) | 0 0 ]      W row = [ hi(w) | hi(w) | lo(w) | 0 0 ]
+// The strided slabs x[5t .. 5t+10) are 10 bytes apart in bf16 -- below TMA's 16-byte stride granularity -- so the
+// A matrix (64 B per frame) is materialised by conv0_im2col_kernel; bias + LayerNorm(512) + GELU run in the epilogue of
+// the full-row tcgen05 tile (tc_gemm variant 514: K-block 32, 64-byte swizzle).
+// ------------------------------------------------------------------------------------------------
+__global__ void conv0_pack_w_kernel(const float* __restrict__ w /*[512][10]*/, bf16* __restrict__ out /*[512][32]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 512 * 32) return;
+  const int n = i >> 5, e = i & 31;
+  float v = 0.f;
+  if (e < 30) {
+    const float x = w[n * 10 + e % 10];
+    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+    v = e < 20 ? hi : x - hi;
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+int conv0_tc_pack_weight(cudaStream_t s, const float* w, bf16* out) {
+  RTDF_REQUIRE(w && out, "conv0_tc_pack_weight: null argument");
+  conv0_pack_w_kernel<<<64, 256, 0, s>>>(w, out);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+__global__ void __launch_bounds__(256)
+conv0_im2col_kernel(const float* __restrict__ wav, int N, int L1, long long rows, bf16* __restrict__ A) {
+  const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (m >= rows) return;
+  const long long b = m / L1;
+  const int t = (int)(m - b * L1);
+  const float* x = wav + b * N + 5 * t;
+  uint32_t hi[5], lo[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float x0 = x[2 * j], x1 = x[2 * j + 1];
+    const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
+    hi[j] = pack_bf16x2(h0, h1);
+    lo[j] = pack_bf16x2(x0 - h0, x1 - h1);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(A + m * 32);
+  dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  dst[1] = make_uint4(hi[4], lo[0], lo[1], lo[2]);
+  dst[2] = make_uint4(lo[3], lo[4], hi[0], hi[1]);
+  dst[3] = make_uint4(hi[2], hi[3], hi[4], 0u);
+}
+
+int conv0_tc_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const bf16* w_packed, const float* bias,
+                     const float* gamma, const float* beta, float eps, bf16* a_scratch, bf16* out_bf16) {
+  RTDF_REQUIRE(wav && w_packed && gamma && beta && a_scratch && out_bf16 && N >= 10 && B > 0, "conv0_tc: bad arguments");
+  const int L1 = (N - 10) / 5 + 1;
+  const long long rows = (long long)B * L1;
+  RTDF_REQUIRE(rows < (1LL << 31), "conv0_tc: too many frames");
+  conv0_im2col_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(wav, N, L1, rows, a_scratch);
+  RTDF_LAUNCH_CHECK();
+  TcOperandA a;
+  a.ptr = a_scratch;
+  a.k_extent = 32;
+  a.rows_per_batch = rows;
+  a.batches = 1;
+  a.row_stride = 32;
+  TcEpilogue e;
+  e.bias = bias;
+  e.act = ACT_GELU;
+  e.ln_gamma = gamma;
+  e.ln_beta = beta;
+  e.ln_eps = eps;
+  e.out_bf16 = out_bf16;
+  e.ld_bf16 = 512;
+  return tc_gemm(s, a, w_packed, 512, 32, TC_PLAIN, 514, e);
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv-0 in fairseq's extractor_mode="default" (wav2vec2-base style; SURVEY.md App. A.2 step 1, alternative):
 //   conv (bias optional) -> GroupNorm(512 groups, 512 channels) = per-(utterance, channel) normalisation over TIME
 //   -> GELU.  The statistics span the whole utterance, so the layer is two sweeps over the (cheap, K = 10) conv:

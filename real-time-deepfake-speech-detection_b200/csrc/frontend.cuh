@@ -15,6 +15,12 @@ int wave_layernorm(cudaStream_t s, const float* x, float* y, int B, int N, float
 int conv0_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w_t, const float* bias,
                   const float* gamma, const float* beta, float eps, float* out_f32, bf16* out_bf16);
 
+// conv-0 as a tcgen05 implicit GEMM (bf16 output, large batches): w_packed [512][32] bf16 from conv0_tc_pack_weight
+// (w: state-dict layout [512][1][10] fp32); a_scratch: B * L1 * 32 bf16 (the hi/lo-split im2col matrix, 64 B per frame).
+int conv0_tc_pack_weight(cudaStream_t s, const float* w, bf16* out);
+int conv0_tc_ln_gelu(cudaStream_t s, const float* wav, int B, int N, const bf16* w_packed, const float* bias,
+                     const float* gamma, const float* beta, float eps, bf16* a_scratch, bf16* out_bf16);
+
 // conv-0 in extractor_mode="default" (group norm): conv (bias may be NULL) -> GroupNorm(512, 512) over time -> GELU.
 // ws: conv0_gn_workspace_floats(B, N) floats of scratch (per-chunk partial statistics + per-utterance scale / shift).
 size_t conv0_gn_workspace_floats(int B, int N);

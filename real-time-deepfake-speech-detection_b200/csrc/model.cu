@@ -158,6 +158,12 @@ static int pack_xlsr(rtdf_ctx* c) {
     RTDF_TRY(dalloc(c, 512LL * ci * f.k, &wp));
     if (i == 0) {
       RTDF_TRY(transpose_f32(0, w, wp, 512, 10));  // [512][10] -> [10][512]
+      if (bf && !c->fe_group_norm) {               // hi/lo-split K = 32 operand of the tensor-core conv-0
+        bf16* w0;
+        RTDF_TRY(dalloc(c, 512LL * 32, &w0));
+        RTDF_TRY(conv0_tc_pack_weight(0, w, w0));
+        c->conv0_tc_w = w0;
+      }
     } else {
       RTDF_TRY(permute_conv_weight(0, w, wp, 512, 512, f.k));  // [co][ci][k] -> [co][k][ci]
     }
@@ -650,6 +656,18 @@ static bool skinny_rows(const rtdf_ctx* c, long long rows) {
   return c->regime != RTDF_REGIME_THROUGHPUT && rows <= kSkinnyRows && skinny_enabled();
 }
 
+// conv-0: tcgen05 implicit GEMM (im2col + full-row LayerNorm tile) once there are enough frames to fill the machine
+// twice over with 128-row tiles; streaming chunks keep the SIMT kernel (32-frame CTAs).  RTDF_CONV0_IMPL=1: SIMT always.
+static bool conv0_tc_wanted(const rtdf_ctx* c, long long frames) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_CONV0_IMPL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  // (the throughput regime never looks at the batch size: per-utterance results must not depend on it)
+  return v == 0 && c->conv0_tc_w && (c->regime == RTDF_REGIME_THROUGHPUT || frames >= 2LL * kNumSMs * 128);
+}
+
 static bool conv_2sm_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -698,6 +716,9 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   if (gn)
     RTDF_TRY(conv0_gn_gelu(s, wav, B, d.N, c->fe[0].lin.w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f, w.gn_ws,
                            bf ? nullptr : static_cast<float*>(w.actA), bf ? static_cast<bf16*>(w.actA) : nullptr));
+  else if (bf && conv0_tc_wanted(c, (long long)B * d.L[0]))   // actB (conv-1's output buffer) is free: im2col scratch
+    RTDF_TRY(conv0_tc_ln_gelu(s, wav, B, d.N, c->conv0_tc_w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f,
+                              static_cast<bf16*>(w.actB), static_cast<bf16*>(w.actA)));
   else
     RTDF_TRY(conv0_ln_gelu(s, wav, B, d.N, c->fe[0].lin.w, c->fe[0].lin.b, c->fe[0].ln.g, c->fe[0].ln.b, 1e-5f,
                            bf ? nullptr : static_cast<float*>(w.actA), bf ? static_cast<bf16*>(w.actA) : nullptr));

@@ -114,6 +114,7 @@ struct rtdf_ctx {
   std::vector<void*> scratch;      // fp32 sources of packed bf16 weights, released at the end of rtdf_finalize
   // XLS-R
   rtdf::FeConv fe[7];
+  const rtdf::bf16* conv0_tc_w = nullptr;   // conv-0 weight as the hi/lo-split [512][32] bf16 operand of the tcgen05 path
   bool fe_group_norm = false;      // fairseq extractor_mode="default" (GroupNorm after conv-0 only), from the state-dict keys
   rtdf::Norm fp_ln;
   rtdf::Lin proj;

@@ -52,6 +52,9 @@ SIGNATURES = {
     "rtdf_preemph": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "rtdf_wave_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "rtdf_conv0_ln_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "rtdf_conv0_tc_scratch_bytes": (c_longlong, [c_int, c_int]),
+    "rtdf_conv0_tc_ln_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                      c_void_p, c_void_p]),
     "rtdf_conv0_gn_workspace_floats": (c_longlong, [c_int, c_int]),
     "rtdf_conv0_gn_gelu": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),

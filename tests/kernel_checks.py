@@ -109,6 +109,44 @@ def check_conv0():
     return out
 
 
+def check_conv0_tc(shapes=((2, 16000), (1, 4003), (3, 64600))):
+    """conv-0 as a tcgen05 implicit GEMM (hi/lo-split K = 32 operands, LN + GELU epilogue) against the fp32 reference.
+    The split keeps the conv itself at ~2^-16 relative, so the error is the bf16 rounding of the output."""
+    from tests.util import native
+    lib = native().load()
+    g = torch.Generator().manual_seed(41)
+    out = {}
+    for B, N in shapes:
+        wav = torch.randn(B, N, generator=g) * 0.1 + 0.03
+        w = torch.randn(512, 1, 10, generator=g) * 0.4
+        b = torch.randn(512, generator=g) * 0.1
+        gamma = 1 + 0.1 * torch.randn(512, generator=g)
+        beta = 0.1 * torch.randn(512, generator=g)
+        if B * N > 2_000_000:
+            _no_tf32()
+            y = F.conv1d(wav.to(DEV).unsqueeze(1), w.to(DEV), b.to(DEV), stride=5)
+            ref = F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma.to(DEV), beta.to(DEV), 1e-5)).cpu()
+        else:
+            y = F.conv1d(wav.unsqueeze(1), w, b, stride=5)
+            ref = F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))
+        L = ref.shape[1]
+        scratch = torch.empty(int(lib.rtdf_conv0_tc_scratch_bytes(B, N)), dtype=torch.uint8, device=DEV)
+        o16 = torch.zeros(B, L, 512, dtype=torch.bfloat16, device=DEV)
+        call("rtdf_conv0_tc_ln_gelu", P(dev(wav)), B, N, P(dev(w.reshape(512, 10).contiguous())), P(dev(b)), P(dev(gamma)),
+             P(dev(beta)), 1e-5, P(scratch), P(o16), stream())
+        got = o16.float().cpu()
+        d16 = float((got - ref).abs().max())
+        # the SIMT kernel's bf16 output of the same layer: both round the same fp32 value, so they agree to one bf16 ulp
+        o_simt = torch.zeros(B, L, 512, dtype=torch.bfloat16, device=DEV)
+        call("rtdf_conv0_ln_gelu", P(dev(wav)), B, N, P(dev(w[:, 0, :].t().contiguous())), P(dev(b)), P(dev(gamma)),
+             P(dev(beta)), 1e-5, None, P(o_simt), stream())
+        d_simt = float((got - o_simt.float().cpu()).abs().max())
+        out[f"{B}x{N}"] = (d16, d_simt)
+        assert d16 <= 0.03, out          # bf16 rounding of O(4) values
+        assert d_simt <= 0.04, out
+    return out
+
+
 def check_conv0_groupnorm():
     """conv-0 of the group-norm feature encoder (fairseq extractor_mode="default"): conv -> GroupNorm(512, 512) over
     time -> GELU, with and without a conv bias, ragged chunk boundaries (L1 = 3199, 799, 256, 257)."""

@@ -28,6 +28,14 @@ def test_conv0_ln_gelu():
     kc.check_conv0()
 
 
+def test_conv0_tcgen05_implicit_gemm():
+    kc.check_conv0_tc()
+
+
+def test_conv0_tcgen05_at_timed_batch():
+    kc.check_conv0_tc(shapes=((64, 64000),))
+
+
 def test_conv0_groupnorm_gelu():
     kc.check_conv0_groupnorm()
 

@@ -203,7 +203,7 @@ attn_map_kernel(const float* __restrict__ x, int H, int W, int Wq, const float* 
 
 int aasist_attn_map(cudaStream_t s, const float* x, int B, int H, int W, const float* w1t, const float* b1,
                     const float* bn_s, const float* bn_t, const float* w2t, const float* b2, float* wmap) {
-  RTDF_REQUIRE(x && wmap && W >= 1 && W <= 96, "attn_map: bad arguments (W = %d)", W);
+  RTDF_REQUIRE(x && wmap && W >= 1 && W <= 128, "attn_map: bad arguments (W = %d)", W);
   const int Wq = ((W + 31) / 32) * 32;
   const size_t smem = (size_t)(64 + 128) * Wq * sizeof(float);
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(attn_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -269,7 +269,7 @@ int aasist_attn_pool(cudaStream_t s, const float* x, const float* wmap, int B, i
 // ------------------------------------------------------------------------------------------------
 // fused graph-attention row: never materialises the (n,n,D) pairwise tensor.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxNodes = 128;
+constexpr int kMaxNodes = 256;
 
 template <int D, int DO>
 __global__ void __launch_bounds__(256)
@@ -430,20 +430,20 @@ graph_pool_kernel(int D, const GraphView h, const float* __restrict__ w, const f
   __shared__ int sidx[kMaxNodes];
   const int b = blockIdx.x, t = threadIdx.x, n = h.n;
   const float* hb = h.ptr + (long long)b * h.batch_stride;
-  if (t < n) {
+  for (int i = t; i < n; i += 128) {
     float z = bptr[0];
-    for (int d = 0; d < D; ++d) z = fmaf(w[d], hb[(long long)t * D + d], z);
-    ss[t] = 1.0f / (1.0f + expf(-z));
+    for (int d = 0; d < D; ++d) z = fmaf(w[d], hb[(long long)i * D + d], z);
+    ss[i] = 1.0f / (1.0f + expf(-z));
   }
   __syncthreads();
-  if (t < n) {
-    const float si = ss[t];
+  for (int i = t; i < n; i += 128) {
+    const float si = ss[i];
     int rank = 0;
     for (int j = 0; j < n; ++j) {
       const float sj = ss[j];
-      rank += (sj > si) || (sj == si && j < t);
+      rank += (sj > si) || (sj == si && j < i);
     }
-    if (rank < k) sidx[rank] = t;
+    if (rank < k) sidx[rank] = i;
   }
   __syncthreads();
   for (int e = t; e < k * D; e += 128) {
@@ -451,7 +451,8 @@ graph_pool_kernel(int D, const GraphView h, const float* __restrict__ w, const f
     const int src = sidx[r];
     out[((long long)b * k + r) * D + d] = hb[(long long)src * D + d] * ss[src];
   }
-  if (idx_out && t < k) idx_out[(long long)b * k + t] = sidx[t];
+  if (idx_out)
+    for (int i = t; i < k; i += 128) idx_out[(long long)b * k + i] = sidx[i];
 }
 
 int aasist_graph_pool(cudaStream_t s, int D, const GraphView& h, int B, const float* w, const float* b, int k,

@@ -43,7 +43,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 
 constexpr int kWarps = 8;
-constexpr int kMaxN = 128;
+constexpr int kMaxN = 256;      // nodes per graph (per-warp score row in shared memory)
 
 template <int D, int DO>
 __global__ void __launch_bounds__(kWarps * 32)

@@ -1082,7 +1082,8 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
   const bool bf = c->d.precision == RTDF_PREC_BF16;
   const long long M = (long long)B * T;
   const int Tp = T / 3, kT = Tp / 2 > 0 ? Tp / 2 : 1, kT2 = kT / 2 > 0 ? kT / 2 : 1;
-  RTDF_REQUIRE(Tp >= 1 && Tp <= 96, "AASIST back-end supports 3..290 frames, got T = %d", T);
+  // T' = T/3 temporal nodes: the shifted-row convs read a slab of 128 + T' + 4 plane rows through one TMA box (<= 256 rows)
+  RTDF_REQUIRE(Tp >= 1 && Tp <= 124, "AASIST back-end supports 3..374 frames (up to 7.4 s of audio), got T = %d", T);
   {
     TcEpilogue e;
     e.bias = a.LL.b;

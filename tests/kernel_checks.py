@@ -526,7 +526,7 @@ def check_graph_pool():
     from oracle.aasist_ref import GraphPool
     out = {}
     torch.manual_seed(7)
-    for B, n, D in ((4, 42, 64), (3, 67, 64), (2, 33, 32), (5, 21, 32), (2, 1, 32), (2, 16, 32)):
+    for B, n, D in ((4, 42, 64), (3, 67, 64), (2, 33, 32), (5, 21, 32), (2, 1, 32), (2, 16, 32), (2, 123, 64), (2, 200, 32)):
         gp = GraphPool(0.5, D).eval()
         h = torch.randn(B, n, D)
         with torch.no_grad():
@@ -580,7 +580,7 @@ def check_gat_rows(impl=0):
     torch.manual_seed(3)
     tol = 2e-5 if impl == 1 else 2e-4
     for B, n, D, DO, temp in ((3, 42, 64, 64, 2.0), (2, 66, 64, 64, 2.0), (2, 16, 64, 64, 2.0), (2, 1, 64, 64, 2.0),
-                              (2, 17, 64, 64, 0.5)):
+                              (2, 17, 64, 64, 0.5), (2, 123, 64, 64, 2.0), (1, 200, 64, 64, 2.0)):
         layer = GraphAttentionLayer(D, DO, temperature=temp).eval()
         perturb_norm_stats(layer, seed=5)
         x = torch.randn(B, n, D)
@@ -594,7 +594,7 @@ def check_gat_rows(impl=0):
         d = float((o.cpu() - ref).abs().max())
         out[f"gat_B{B}_n{n}"] = d
         assert d <= tol, out
-    for B, n1, n2, D, DO, temp in ((3, 33, 21, 64, 32, 100.0), (2, 16, 10, 32, 32, 100.0), (2, 5, 3, 64, 32, 1.0),
+    for B, n1, n2, D, DO, temp in ((3, 33, 21, 64, 32, 100.0), (2, 16, 10, 32, 32, 100.0), (2, 5, 3, 64, 32, 1.0), (2, 61, 21, 64, 32, 100.0),
                                    (2, 1, 1, 32, 32, 100.0)):
         layer = HtrgGraphAttentionLayer(D, DO, temperature=temp).eval()
         perturb_norm_stats(layer, seed=6)

@@ -1102,29 +1102,50 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
   } else {
     RTDF_TRY(run_aasist_encoder_simt(c, s, B, Tp, w));
   }
+  // The spectral and the temporal graph, and later the two heterogeneous branches, are independent until the read-out:
+  // they run on two streams (fork / join through events -- capturable, ordered with respect to the caller's stream), so
+  // their small latency-bound kernels overlap instead of queueing behind each other.
+  cudaStream_t s2 = c->side_stream ? c->side_stream : s;
+  auto fork = [&]() -> int {
+    if (s2 == s) return RTDF_OK;
+    RTDF_CHECK_CUDA(cudaEventRecord(c->ev_fork, s));
+    RTDF_CHECK_CUDA(cudaStreamWaitEvent(s2, c->ev_fork, 0));
+    return RTDF_OK;
+  };
+  auto join = [&]() -> int {
+    if (s2 == s) return RTDF_OK;
+    RTDF_CHECK_CUDA(cudaEventRecord(c->ev_join, s2));
+    RTDF_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+    return RTDF_OK;
+  };
+  RTDF_TRY(fork());
   RTDF_TRY(gat_rows(c, s, 64, 64, view(w.eS, 42, 42 * 64), B, 42, a.gat_S, w.gS, 42 * 64, nullptr, 0, nullptr, nullptr));
-  RTDF_TRY(gat_rows(c, s, 64, 64, view(w.eT, Tp, (long long)Tp * 64), B, Tp, a.gat_T, w.gT, (long long)Tp * 64, nullptr, 0, nullptr, nullptr));
   RTDF_TRY(aasist_graph_pool(s, 64, view(w.gS, 42, 42 * 64), B, a.pool_S.w, a.pool_S.b, 21, w.oS, w.idxS));
-  RTDF_TRY(aasist_graph_pool(s, 64, view(w.gT, Tp, (long long)Tp * 64), B, a.pool_T.w, a.pool_T.b, kT, w.oT, w.idxT));
+  RTDF_TRY(gat_rows(c, s2, 64, 64, view(w.eT, Tp, (long long)Tp * 64), B, Tp, a.gat_T, w.gT, (long long)Tp * 64, nullptr, 0, nullptr, nullptr));
+  RTDF_TRY(aasist_graph_pool(s2, 64, view(w.gT, Tp, (long long)Tp * 64), B, a.pool_T.w, a.pool_T.b, kT, w.oT, w.idxT));
+  RTDF_TRY(join());
   const HsGalW* l1[2] = {&a.st11, &a.st21};
   const HsGalW* l2[2] = {&a.st12, &a.st22};
   const PoolW* pS[2] = {&a.pool_hS1, &a.pool_hS2};
   const PoolW* pT[2] = {&a.pool_hT1, &a.pool_hT2};
   const float* master[2] = {a.master1, a.master2};
   const int n = kT + 21, n2 = kT2 + 10;
+  RTDF_TRY(fork());
   for (int i = 0; i < 2; ++i) {
     const AasistWs::Br& r = w.br[i];
-    RTDF_TRY(aasist_type_proj(s, 64, view(w.oT, kT, (long long)kT * 64), view(w.oS, 21, 21 * 64), B, l1[i]->t1_wt,
+    cudaStream_t sb = i == 0 ? s : s2;
+    RTDF_TRY(aasist_type_proj(sb, 64, view(w.oT, kT, (long long)kT * 64), view(w.oS, 21, 21 * 64), B, l1[i]->t1_wt,
                               l1[i]->t1_b, l1[i]->t2_wt, l1[i]->t2_b, r.hx));
-    RTDF_TRY(gat_rows(c, s, 64, 32, view(r.hx, n, (long long)n * 64), B, kT, l1[i]->rows, r.hy, (long long)n * 32,
+    RTDF_TRY(gat_rows(c, sb, 64, 32, view(r.hx, n, (long long)n * 64), B, kT, l1[i]->rows, r.hy, (long long)n * 32,
                              master[i], 0, &l1[i]->master, r.ma));
-    RTDF_TRY(aasist_graph_pool(s, 32, view(r.hy + (long long)kT * 32, 21, (long long)n * 32), B, pS[i]->w, pS[i]->b, 10, r.pS, nullptr));
-    RTDF_TRY(aasist_graph_pool(s, 32, view(r.hy, kT, (long long)n * 32), B, pT[i]->w, pT[i]->b, kT2, r.pT, nullptr));
-    RTDF_TRY(aasist_type_proj(s, 32, view(r.pT, kT2, (long long)kT2 * 32), view(r.pS, 10, 10 * 32), B, l2[i]->t1_wt,
+    RTDF_TRY(aasist_graph_pool(sb, 32, view(r.hy + (long long)kT * 32, 21, (long long)n * 32), B, pS[i]->w, pS[i]->b, 10, r.pS, nullptr));
+    RTDF_TRY(aasist_graph_pool(sb, 32, view(r.hy, kT, (long long)n * 32), B, pT[i]->w, pT[i]->b, kT2, r.pT, nullptr));
+    RTDF_TRY(aasist_type_proj(sb, 32, view(r.pT, kT2, (long long)kT2 * 32), view(r.pS, 10, 10 * 32), B, l2[i]->t1_wt,
                               l2[i]->t1_b, l2[i]->t2_wt, l2[i]->t2_b, r.hx2));
-    RTDF_TRY(gat_rows(c, s, 32, 32, view(r.hx2, n2, (long long)n2 * 32), B, kT2, l2[i]->rows, r.hy2, (long long)n2 * 32,
+    RTDF_TRY(gat_rows(c, sb, 32, 32, view(r.hx2, n2, (long long)n2 * 32), B, kT2, l2[i]->rows, r.hy2, (long long)n2 * 32,
                              r.ma, 32, &l2[i]->master, r.mb));
   }
+  RTDF_TRY(join());
   ReadoutArgs ro;
   ro.T1 = view(w.br[0].pT, kT2, (long long)kT2 * 32);
   ro.Ta1 = view(w.br[0].hy2, kT2, (long long)n2 * 32);
@@ -1305,6 +1326,14 @@ int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc) {
   if (c->d.conf_heads == 0) c->d.conf_heads = 4;
   if (c->d.conf_kernel == 0) c->d.conf_kernel = 31;
   if (c->d.conf_blocks == 0) c->d.conf_blocks = 4;
+  {  // second stream + fork / join events for the independent graph branches of the AASIST back-end (RTDF_BRANCH_STREAMS=0: off)
+    const char* e = getenv("RTDF_BRANCH_STREAMS");
+    if (!(e && e[0] == '0') && c->d.backend == RTDF_BACKEND_AASIST) {
+      RTDF_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+      RTDF_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      RTDF_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+  }
   *out = c;
   return RTDF_OK;
 }
@@ -1374,6 +1403,9 @@ void rtdf_destroy(rtdf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (void* p : c->owned) cudaFree(p);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   delete c;
 }
 

@@ -109,6 +109,8 @@ struct rtdf_ctx {
   rtdf_model_desc d{};
   bool finalized = false;
   int regime = RTDF_REGIME_AUTO;   // rtdf_set_regime
+  cudaStream_t side_stream = nullptr;   // AASIST back-end: second stream for the independent graph branches
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::string, rtdf::Raw> raw;
   std::vector<void*> owned;
   std::vector<void*> scratch;      // fp32 sources of packed bf16 weights, released at the end of rtdf_finalize

@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--sweep-utterances", type=int, default=SWEEP_UTTERANCES)
     ap.add_argument("--latency-calls", type=int, default=1000)
+    ap.add_argument("--warm-seconds", type=float, default=1.0,
+                    help="untimed steps after the W warm-up steps, so the clocks settle where a long job holds them")
     return ap.parse_args()
 
 
@@ -351,7 +353,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     extra_warm = 0
     t_w = time.time()
-    while time.time() - t_w < 1.0:
+    while time.time() - t_w < args.warm_seconds:
         for i in range(8):
             eng.forward(inputs[i % n_bufs])
         torch.cuda.synchronize()

@@ -139,6 +139,23 @@ int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const floa
 int rtdf_gemm_bf16_rowln(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout,
                          const float* gamma, const float* beta, float eps, void* ln_out_bf16, float* ln_out_f32,
                          int32_t* counters, int variant, void* stream);
+/* LayerNorm folded into the GEMMs on either side of it -- how the bf16 transformer layers run (the two LayerNorms of
+ * fairseq's TransformerSentenceEncoderLayer never execute as kernels):
+ *   LN(x) W^T + b  ==  rstd_i * (bf16(x) W'^T - mean_i * c) + d,   W' = bf16(W diag(gamma)), c_j = sum_k W'_jk, d = b + W beta.
+ * rtdf_fold_ln_weight   packs W (n,k fp32), gamma, beta, bias -> W' (bf16), c, d.
+ * rtdf_gemm_bf16_xres   residual GEMM x (M,N fp32) += A W^T + bias that also emits bf16(x) and, per row, 8 partial
+ *                       (sum, sum of squares) pairs -- stats (M, 8, 2) fp32, slot = 256-column tile * 2 + half; variant 256 |
+ *                       2256, N = 1024 fills all 8 slots (smaller N: zero the buffer first).
+ * rtdf_cast_stats_rows  the same two outputs from a resident row (N = 1024): xb = bf16(x), totals in slot 0, slots 1..7
+ *                       zero; n_splits > 0 first adds the K-split partial sums like rtdf_layernorm_accum_rows.
+ * rtdf_gemm_bf16_lnfold out = act(rstd_i * (xb W'^T - mean_i c) + d), row statistics over K columns from the 8 partials. */
+int rtdf_fold_ln_weight(const float* w, const float* gamma, const float* beta, const float* bias, int n, int k, void* w_folded,
+                        float* c, float* d, void* stream);
+int rtdf_gemm_bf16_xres(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout, void* xb_out,
+                        float* stats_out, int variant, void* stream);
+int rtdf_cast_stats_rows(float* x, const float* partials, int n_splits, long long rows, void* xb, float* stats, void* stream);
+int rtdf_gemm_bf16_lnfold(const void* xb, const void* W_folded, int M, int N, int K, const float* c, const float* d,
+                          const float* stats, float eps, int act, float* out_f32, void* out_bf16, int variant, void* stream);
 /* Skinny GEMMs of streaming chunks (batch 1-8 x 1 s: M = 49..392 rows): the op is a weight stream, so K is split over
  * the otherwise idle SMs.  rtdf_gemm_plan_splits gives the number of splits S for a shape (1 = not split);
  * rtdf_gemm_bf16_splitk (S > 1 only) writes split s's partial sum of A W^T (+ bias on split 0) to

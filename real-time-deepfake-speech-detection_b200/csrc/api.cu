@@ -88,6 +88,48 @@ int rtdf_gemm_bf16(const void* A, const void* W, int M, int N, int K, const floa
                  make_epi(bias, act, scale, resid, out_f32, out_bf16, N));
 }
 
+int rtdf_gemm_bf16_xres(const void* A, const void* W, int M, int N, int K, const float* bias, float* x_inout, void* xb_out,
+                        float* stats_out, int variant, void* stream) {
+  RTDF_REQUIRE(A && W && x_inout && xb_out && stats_out, "rtdf_gemm_bf16_xres: null argument");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(A);
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  TcEpilogue e = make_epi(bias, ACT_NONE, 1.0f, x_inout, x_inout, nullptr, N);
+  e.xb_out = static_cast<bf16*>(xb_out);
+  e.stats_out = reinterpret_cast<float2*>(stats_out);
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W), N, K, TC_PLAIN, variant, e);
+}
+
+int rtdf_gemm_bf16_lnfold(const void* xb, const void* W_folded, int M, int N, int K, const float* c, const float* d,
+                          const float* stats, float eps, int act, float* out_f32, void* out_bf16, int variant, void* stream) {
+  RTDF_REQUIRE(xb && W_folded && c && d && stats && (out_f32 || out_bf16), "rtdf_gemm_bf16_lnfold: null argument");
+  TcOperandA a;
+  a.ptr = static_cast<const bf16*>(xb);
+  a.k_extent = K;
+  a.rows_per_batch = M;
+  a.batches = 1;
+  a.row_stride = K;
+  TcEpilogue e = make_epi(d, act, 1.0f, nullptr, out_f32, out_bf16, N);
+  e.fold_c = c;
+  e.fold_stats = reinterpret_cast<const float2*>(stats);
+  e.fold_len = K;
+  e.fold_eps = eps;
+  return tc_gemm(static_cast<cudaStream_t>(stream), a, static_cast<const bf16*>(W_folded), N, K, TC_PLAIN, variant, e);
+}
+
+int rtdf_cast_stats_rows(float* x, const float* partials, int n_splits, long long rows, void* xb, float* stats, void* stream) {
+  return cast_stats_rows(static_cast<cudaStream_t>(stream), x, partials, n_splits, rows, static_cast<bf16*>(xb),
+                         reinterpret_cast<float2*>(stats));
+}
+
+int rtdf_fold_ln_weight(const float* w, const float* gamma, const float* beta, const float* bias, int n, int k, void* w_folded,
+                        float* c, float* d, void* stream) {
+  return fold_ln_weight(static_cast<cudaStream_t>(stream), w, gamma, beta, bias, n, k, static_cast<bf16*>(w_folded), c, d);
+}
+
 int rtdf_gemm_plan_splits(int M, int N, int K) { return tc_plan_splits(M, N, K); }
 
 int rtdf_gemm_bf16_splitk(const void* A, const void* W, int M, int N, int K, const float* bias, float* partials,

@@ -194,9 +194,11 @@ struct AttWsParams {
   int debug;
 };
 
+template <bool kLong>      // kLong: 256 < T <= 512 (single 512-column TMEM buffer); compile-time so the usual path keeps constants
 __global__ void __launch_bounds__(kWsThreads, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                     bf16* __restrict__ ctx, const AttWsParams p) {
+  constexpr int kNb = kLong ? 1 : 2, kBufCols = kLong ? 512 : 256, kOCol = kLong ? 448 : 128, kKvBoxes = kLong ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -255,7 +257,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         mbar_expect_tx(full_bar(s), 16384u + 2u * p.kv_bytes);
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384, sV = sK + p.kv_bytes;
         tma_load_3d(sQ, &mapQ, full_bar(s), h * 64, qt * 128, b);
-        for (int bx = 0; bx < p.kv_boxes; ++bx) {
+#pragma unroll
+        for (int bx = 0; bx < kKvBoxes; ++bx) {
           tma_load_3d(sK + bx * 32768, &mapKV, full_bar(s), HD + h * 64, bx * 256, b);
           tma_load_3d(sV + bx * 32768, &mapKV, full_bar(s), 2 * HD + h * 64, bx * 256, b);
         }
@@ -269,13 +272,13 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const uint32_t idesc_s2 = n2 > 0 ? umma_idesc_bf16(128, n2) : 0u;
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, /*a_mn=*/0, /*b_mn=*/1);
       const int ksteps = p.Tk / 16;
-      const int nb = p.n_buf;
+      constexpr int nb = kNb;
       auto issue_pv = [&](int j) {
         const int g = j % nb, s = j % p.n_stages;
         mbar_wait(pfull_bar(g), (j / nb) & 1);
         tc_fence_after();
         const uint32_t sV = base + s * p.stage_bytes + 16384 + p.kv_bytes;
-        const uint32_t tP = tmem + g * p.buf_cols, tO = tP + p.o_col;
+        const uint32_t tP = tmem + g * kBufCols, tO = tP + kOCol;
         for (int ks = 0; ks < ksteps && !(p.debug & 16); ++ks)
           mma_bf16_ts(tO, tP + ks * 8, umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
         mma_commit(empty_bar(s));     // Q, K, V of this stage are no longer read
@@ -290,9 +293,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (!(p.debug & 8)) {
-            mma_bf16_ss(tmem + g * p.buf_cols, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
-            if (n2 > 0)
-              mma_bf16_ss(tmem + g * p.buf_cols + 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + 32768 + k * 32),
+            mma_bf16_ss(tmem + g * kBufCols, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + k * 32), idesc_s, k != 0);
+            if (kLong && n2 > 0)
+              mma_bf16_ss(tmem + g * kBufCols + 256, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + 32768 + k * 32),
                           idesc_s2, k != 0);
           }
         mma_commit(sfull_bar(g));
@@ -307,9 +310,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;                      // TMEM lane quarter of this warp
     const int r = q * 32 + lane;                 // row inside the query tile
-    const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + g * p.buf_cols;
+    const uint32_t t_row = tmem + (static_cast<uint32_t>(q * 32) << 16) + g * kBufCols;
     const int T = p.T;
-    const int nb = p.n_buf;
+    constexpr int nb = kNb;
     const float kLog2e = 1.4426950408889634f;
     for (int i = g; i < n_local && g < nb; i += nb) {
       const int item = blockIdx.x + i * gridDim.x;
@@ -396,8 +399,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const float inv = 1.0f / sum;
         const int tq = qt * 128 + r;
         uint32_t v0[32], v1[32];
-        tmem_ld32(t_row + p.o_col, v0);
-        tmem_ld32(t_row + p.o_col + 32, v1);
+        tmem_ld32(t_row + kOCol, v0);
+        tmem_ld32(t_row + kOCol + 32, v1);
         tmem_ld_wait();
         if (tq < T) {
           bf16* dst = ctx + ((long long)b * T + tq) * HD + h * 64;
@@ -468,9 +471,14 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   uint32_t boxkv[3] = {64, (uint32_t)(long_mode ? 256 : p.Tk), 1};
   RTDF_TRY(make_tmap_bf16(&mapQ, qkv, 3, dims, strides, boxq, TMAP_SW128));
   RTDF_TRY(make_tmap_bf16(&mapKV, qkv, 3, dims, strides, boxkv, TMAP_SW128));
-  RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_ws_kernel), (size_t)smem));
   const int grid = p.total_items < kNumSMs ? p.total_items : kNumSMs;
-  RTDF_CHECK_CUDA(launch_pdl(attention_ws_kernel, dim3(grid), dim3(kWsThreads), smem, s, mapQ, mapKV, ctx, p));
+  if (long_mode) {
+    RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_ws_kernel<true>), (size_t)smem));
+    RTDF_CHECK_CUDA(launch_pdl(attention_ws_kernel<true>, dim3(grid), dim3(kWsThreads), smem, s, mapQ, mapKV, ctx, p));
+  } else {
+    RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&attention_ws_kernel<false>), (size_t)smem));
+    RTDF_CHECK_CUDA(launch_pdl(attention_ws_kernel<false>, dim3(grid), dim3(kWsThreads), smem, s, mapQ, mapKV, ctx, p));
+  }
   RTDF_LAUNCH_CHECK();
   return RTDF_OK;
 }

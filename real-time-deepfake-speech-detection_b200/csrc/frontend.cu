@@ -597,6 +597,88 @@ ln1024_accum_kernel(float* __restrict__ x, const float* __restrict__ partials, i
   }
 }
 
+// Folded-LayerNorm companion of the two kernels above (gemm_tc.cuh, TcEpilogue::fold_*): the GEMM that follows applies
+// the normalisation in its epilogue, so this kernel only (optionally) folds the K-split partial sums into the residual
+// row, and emits the row as bf16 plus its (sum, sum of squares) in slot 0 of the 8 statistics slots (slots 1..7 zero).
+template <bool kAccum>
+__global__ void __launch_bounds__(128)
+cast_stats1024_kernel(float* __restrict__ x, const float* __restrict__ partials, int n_splits, long long split_stride,
+                      bf16* __restrict__ xb, float2* __restrict__ stats) {
+  __shared__ float red[2][4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  float* xr = x + row * 1024 + t * 8;
+  float4 v0 = *reinterpret_cast<const float4*>(xr), v1 = *reinterpret_cast<const float4*>(xr + 4);
+  if (kAccum) {
+    const float* pr = partials + row * 1024 + t * 8;
+#pragma unroll 4
+    for (int sp = 0; sp < n_splits; ++sp) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(pr + sp * split_stride));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(pr + sp * split_stride + 4));
+      v0.x += a.x; v0.y += a.y; v0.z += a.z; v0.w += a.w;
+      v1.x += b.x; v1.y += b.y; v1.z += b.z; v1.w += b.w;
+    }
+    *reinterpret_cast<float4*>(xr) = v0;
+    *reinterpret_cast<float4*>(xr + 4) = v1;
+  }
+  const float s = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w));
+  const float q = warp_sum(v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z +
+                           v1.w * v1.w);
+  if (lane == 0) { red[0][wid] = s; red[1][wid] = q; }
+  *reinterpret_cast<uint4*>(xb + row * 1024 + t * 8) =
+      make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+  __syncthreads();
+  if (t < 8)
+    stats[row * 8 + t] = t == 0 ? make_float2((red[0][0] + red[0][1]) + (red[0][2] + red[0][3]),
+                                              (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]))
+                                : make_float2(0.f, 0.f);
+}
+
+int cast_stats_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, bf16* xb, float2* stats) {
+  RTDF_REQUIRE(x && xb && stats && rows > 0 && (n_splits == 0 || partials), "cast_stats_rows: bad arguments");
+  const unsigned g = (unsigned)rows;
+  if (n_splits > 0)
+    RTDF_CHECK_CUDA(launch_pdl(cast_stats1024_kernel<true>, dim3(g), dim3(128), 0, s, x, partials, n_splits, rows * 1024, xb, stats));
+  else
+    RTDF_CHECK_CUDA(launch_pdl(cast_stats1024_kernel<false>, dim3(g), dim3(128), 0, s, x, partials, n_splits, rows * 1024, xb, stats));
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
+// W' = bf16(W diag(gamma)), c_j = sum_k W'_jk (of the ROUNDED values: exactly what the tensor core multiplies with),
+// d_j = bias_j + sum_k beta_k W_jk.  One warp per output row.
+__global__ void __launch_bounds__(256)
+fold_ln_weight_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ bias, int n, int k, bf16* __restrict__ wb, float* __restrict__ c,
+                      float* __restrict__ d) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= n) return;
+  float cs = 0.f, ds = 0.f;
+  for (int kk = lane; kk < k; kk += 32) {
+    const float wv = w[(long long)j * k + kk];
+    const bf16 r = __float2bfloat16_rn(wv * gamma[kk]);
+    wb[(long long)j * k + kk] = r;
+    cs += __bfloat162float(r);
+    ds = fmaf(beta[kk], wv, ds);
+  }
+  cs = warp_sum(cs);
+  ds = warp_sum(ds);
+  if (lane == 0) {
+    c[j] = cs;
+    d[j] = (bias ? bias[j] : 0.f) + ds;
+  }
+}
+
+int fold_ln_weight(cudaStream_t s, const float* w, const float* gamma, const float* beta, const float* bias, int n, int k,
+                   bf16* wb, float* c, float* d) {
+  RTDF_REQUIRE(w && gamma && beta && wb && c && d && n > 0 && k > 0, "fold_ln_weight: bad arguments");
+  fold_ln_weight_kernel<<<ceil_div(n, 8), 256, 0, s>>>(w, gamma, beta, bias, n, k, wb, c, d);
+  RTDF_LAUNCH_CHECK();
+  return RTDF_OK;
+}
+
 int layernorm_accum_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, const float* gamma,
                          const float* beta, float eps, float* out_f32, bf16* out_bf16) {
   RTDF_REQUIRE(x && partials && n_splits >= 1 && rows > 0 && gamma && beta && ((out_f32 != nullptr) != (out_bf16 != nullptr)),

@@ -38,6 +38,14 @@ int layernorm_rows_bf16(cudaStream_t s, const bf16* in, long long rows, int C, c
 int layernorm_accum_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, const float* gamma,
                          const float* beta, float eps, float* out_f32, bf16* out_bf16);
 
+// Folded LayerNorm (gemm_tc.cuh, TcEpilogue::fold_* / xb_out / stats_out): row (1024 wide) -> bf16 copy + per-row
+// (sum, sum of squares) in slot 0 of stats[row][8] (slots 1..7 zeroed); n_splits > 0 first folds the K-split partial sums
+// into x like layernorm_accum_rows.
+int cast_stats_rows(cudaStream_t s, float* x, const float* partials, int n_splits, long long rows, bf16* xb, float2* stats);
+// W' = bf16(W diag(gamma)) [n][k], c[j] = sum_k W'[j][k], d[j] = bias[j] + sum_k beta[k] W[j][k]
+int fold_ln_weight(cudaStream_t s, const float* w, const float* gamma, const float* beta, const float* bias, int n, int k,
+                   bf16* wb, float* c, float* d);
+
 // fp32 verification path of the grouped positional conv: x (B,T,1024) fp32, w packed [1024][128*64]
 // (k index = tap*64 + ci), out x += gelu(conv + bias)
 int posconv_f32(cudaStream_t s, float* x, const float* xin, int B, int T, const float* w_packed, const float* bias);

@@ -27,6 +27,7 @@ enum EpiMode {
   EPI_TMA_F32 = 1,      // out_f32 = v                (TMA store)
   EPI_TMA_F32_ADD = 2,  // out_f32 += v               (TMA reduce-add; in-place residual)
   EPI_TMA_BF16 = 3,     // out_bf16 = v               (TMA store)
+  EPI_XRES = 4,         // out_f32 = x_old + v (x_old read by the SM, TMA store) + bf16 copy + per-row partial statistics
 };
 
 struct TcKernelParams {
@@ -123,13 +124,55 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, int bk) {
   return d;
 }
 
-// v = act(acc + bias) * scale for 32 consecutive columns of this thread's row
-__device__ __forceinline__ void epilogue_math32(const TcEpilogue& e, const uint32_t* acc, const float* s_bias, float* o) {
+// Per-thread (= per output row) state of a folded LayerNorm: v = acc * rstd + (nmr * c_j + bias_j), nmr = -mean * rstd
+struct LnFold {
+  const float* c = nullptr;   // global, column 0 of the output (nullptr: no fold)
+  float rstd = 1.f, nmr = 0.f;
+};
+
+__device__ __forceinline__ LnFold ln_fold_row(const TcEpilogue& e, long long row, bool row_ok) {
+  LnFold f;
+  if (!e.fold_stats) return f;
+  f.c = e.fold_c;
+  if (row_ok) {
+    const float4* st = reinterpret_cast<const float4*>(e.fold_stats + row * 8);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {      // fixed order: the statistics do not depend on who wrote which slot first
+      const float4 v = st[i];
+      s += v.x; q += v.y;
+      s += v.z; q += v.w;
+    }
+    const float inv_n = 1.0f / (float)e.fold_len;
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    f.rstd = rsqrtf(var + e.fold_eps);
+    f.nmr = -mean * f.rstd;
+  }
+  return f;
+}
+
+// v = act(acc + bias) * scale for 32 consecutive columns of this thread's row (col = first of them in the output)
+__device__ __forceinline__ void epilogue_math32(const TcEpilogue& e, const uint32_t* acc, const float* s_bias, float* o,
+                                                const LnFold& fold = LnFold(), int col = 0) {
   float2* o2 = reinterpret_cast<float2*>(o);
   const float2* b2 = reinterpret_cast<const float2*>(s_bias);
+  if (fold.c) {
+    const float4* c4 = reinterpret_cast<const float4*>(fold.c + col);     // same address in every lane: broadcast loads
+    const float2 r2 = make_float2(fold.rstd, fold.rstd), m2 = make_float2(fold.nmr, fold.nmr);
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    o2[i] = add2(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])), b2[i]);
+    for (int i = 0; i < 8; ++i) {
+      const float4 cv = __ldg(c4 + i);
+      o2[2 * i] = fma2(make_float2(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1])), r2,
+                       fma2(m2, make_float2(cv.x, cv.y), b2[2 * i]));
+      o2[2 * i + 1] = fma2(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), r2,
+                           fma2(m2, make_float2(cv.z, cv.w), b2[2 * i + 1]));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      o2[i] = add2(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])), b2[i]);
+  }
   if (e.act == ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) o2[i] = gelu2(o2[i]);
@@ -203,10 +246,61 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* box, int lane, const flo
 template <int BN>
 __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, const CUtensorMap* mapC, int mode, uint32_t t_row,
                                                     const float* sb, int half, int lane, uint8_t* box_gen, uint32_t box,
-                                                    int n0, int row0, int batch, long long row, bool row_ok) {
+                                                    int n0, int row0, int batch, long long row, bool row_ok,
+                                                    const LnFold& fold, int n_tile) {
   constexpr int kColsPerWarp = BN / 2;
   const int c_begin = half * kColsPerWarp, c_end = c_begin + kColsPerWarp;
-  if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
+  if (mode == EPI_XRES) {
+    // x_new = x_old + v: x_old is read by this thread (its own row), x_new goes back through TMA stores, its bf16 copy and
+    // this thread's partial (sum, sum of squares) over its columns go out with plain stores.
+    if constexpr (kColsPerWarp >= 32) {
+      const float* xr = p.epi.resid + row * p.epi.ldr + n0;
+      bf16* xb = p.epi.xb_out + row * (long long)p.N + n0;
+      float s_sum = 0.f, s_sq = 0.f;
+      float4 xo[8];
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xo[i] = *reinterpret_cast<const float4*>(xr + c_begin + 4 * i);
+      }
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+        __align__(16) float o[32];
+        epilogue_math32(p.epi, r, sb + c, o, fold, n0 + c);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[4 * i] += xo[i].x; o[4 * i + 1] += xo[i].y; o[4 * i + 2] += xo[i].z; o[4 * i + 3] += xo[i].w;
+          }
+          if (c + 32 < c_end) {       // next chunk's x_old: in flight while this one is staged and stored
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xo[i] = *reinterpret_cast<const float4*>(xr + c + 32 + 4 * i);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s_sum += o[i];
+            s_sq = fmaf(o[i], o[i], s_sq);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(xb + c + i) = make_uint4(pack_bf16x2(o[i], o[i + 1]), pack_bf16x2(o[i + 2], o[i + 3]),
+                                                               pack_bf16x2(o[i + 4], o[i + 5]), pack_bf16x2(o[i + 6], o[i + 7]));
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        stage_row_f32(box_gen, lane, o);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < p.rows_per_batch) {
+          tma_store_3d(mapC, box, n0 + c, row0, batch);
+          tma_store_commit();
+        }
+      }
+      if (row_ok) p.epi.stats_out[row * 8 + n_tile * 2 + half] = make_float2(s_sum, s_sq);
+    }
+  } else if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 64) {
       if (n0 + c >= p.N) break;  // warp-uniform
@@ -214,9 +308,9 @@ __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, con
       tmem_ld32(t_row + c, r0);
       tmem_ld32(t_row + c + 32, r1);
       tmem_ld_wait();
-      __align__(8) float o[64];
-      epilogue_math32(p.epi, r0, sb + c, o);
-      epilogue_math32(p.epi, r1, sb + c + 32, o + 32);
+      __align__(16) float o[64];
+      epilogue_math32(p.epi, r0, sb + c, o, fold, n0 + c);
+      epilogue_math32(p.epi, r1, sb + c + 32, o + 32, fold, n0 + c + 32);
       if (lane == 0) tma_store_wait_read<0>();   // previous store out of this box has drained
       __syncwarp();
       stage_row_bf16(box_gen, lane, o);
@@ -234,8 +328,8 @@ __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, con
       uint32_t r[32];
       tmem_ld32(t_row + c, r);
       tmem_ld_wait();
-      __align__(8) float o[32];
-      epilogue_math32(p.epi, r, sb + c, o);
+      __align__(16) float o[32];
+      epilogue_math32(p.epi, r, sb + c, o, fold, n0 + c);
       if (mode == EPI_TMA_F32 || mode == EPI_TMA_F32_ADD) {
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
@@ -501,13 +595,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           sb[i] = (p.epi.bias && split == 0 && n0 + i < p.N) ? p.epi.bias[n0 + i] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
+      const LnFold fold = kLN ? LnFold() : ln_fold_row(p.epi, row, row_ok);   // row statistics: fetched ahead of the accumulator
       mbar_wait(tfull_bar(a), aph);
       __syncwarp();
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (kLN ? 0 : a * BN);
       if (!kLN) {
         epilogue_plain_tile<BN>(p, &mapC, mode, t_row, s_params + a * BN, half, lane, box_gen, box, n0, row0,
-                                p.k_splits > 1 ? split : batch, row, row_ok);
+                                p.k_splits > 1 ? split : batch, row, row_ok, fold, n_tile);
       } else {
         // y = act(LayerNorm_512(acc + bias)).  Two warps share a row (256 columns each): one TMEM pass for
         // (sum, sum of squares), partials exchanged through smem, one pass to normalise / activate / store.
@@ -748,12 +843,13 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       float* sb = s_params + a * BN;
       for (int i = et; i < BN; i += kEpiThreads) sb[i] = (p.epi.bias && n0 + i < p.N) ? p.epi.bias[n0 + i] : 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      const LnFold fold = ln_fold_row(p.epi, row, row_ok);      // row statistics: fetched ahead of the accumulator
       mbar_wait(tfull_bar(a), aph);
       __syncwarp();
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
       if (!(p.debug & 4))
-        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok);
+        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok, fold, n_tile);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
@@ -1277,7 +1373,14 @@ static int choose_epilogue_mode(TcKernelParams& p, CUtensorMap* mapC, const CUte
                        (reinterpret_cast<uintptr_t>(epi.out_f32) % 16 == 0);
   const bool one_bf16 = epi.out_bf16 && !epi.out_f32 && !epi.resid && (epi.ld_bf16 % 8 == 0) &&
                         (reinterpret_cast<uintptr_t>(epi.out_bf16) % 16 == 0);
-  if (ln_variant) {
+  if (epi.xb_out) {
+    RTDF_REQUIRE(!ln_variant && BN >= 64 && one_f32 && epi.resid == epi.out_f32 && epi.ldr == epi.ld_f32 && epi.ld_f32 == N &&
+                 N % BN == 0 && N / BN * 2 <= 8 && A.batches == 1 && epi.stats_out && !epi.partials && !epi.rowln_counters &&
+                 (reinterpret_cast<uintptr_t>(epi.xb_out) % 16 == 0),
+                 "tc_gemm: the bf16-copy + row-statistics epilogue needs an in-place fp32 residual with dense rows, "
+                 "N a multiple of the tile width and at most 8 (tile, half) slots per row");
+    p.epi_mode = EPI_XRES;
+  } else if (ln_variant) {
     RTDF_REQUIRE(one_bf16, "tc_gemm: the LayerNorm variant writes exactly one bf16 output (16-byte aligned rows)");
     p.epi_mode = EPI_TMA_BF16;
   } else if (!force_direct_epilogue()) {
@@ -1285,7 +1388,11 @@ static int choose_epilogue_mode(TcKernelParams& p, CUtensorMap* mapC, const CUte
     else if (one_f32 && epi.resid == epi.out_f32 && epi.ldr == epi.ld_f32) p.epi_mode = EPI_TMA_F32_ADD;
     else if (one_bf16 && BN >= 128) p.epi_mode = EPI_TMA_BF16;
   }
-  if (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD) {
+  if (epi.fold_stats)
+    RTDF_REQUIRE(epi.fold_c && N % 32 == 0 && A.batches == 1 && !ln_variant && !epi.partials &&
+                 (reinterpret_cast<uintptr_t>(epi.fold_c) % 16 == 0) && (reinterpret_cast<uintptr_t>(epi.fold_stats) % 16 == 0),
+                 "tc_gemm: folded LayerNorm needs column sums, N a multiple of 32 and one batch");
+  if (p.epi_mode == EPI_TMA_F32 || p.epi_mode == EPI_TMA_F32_ADD || p.epi_mode == EPI_XRES) {
     uint64_t dims[3] = {(uint64_t)N, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
     uint64_t strides[2] = {(uint64_t)epi.ld_f32 * 4, (uint64_t)epi.ld_f32 * 4 * (uint64_t)A.rows_per_batch};
     uint32_t box[3] = {32, 32, 1};

@@ -22,6 +22,21 @@ struct TcEpilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
+  // ---- LayerNorm folded into the GEMMs on either side of it (bf16 transformer layers, model.cu) -------------------
+  // y = LN(x) W^T + b  ==  rstd_i * (bf16(x) W'^T - mean_i * c) + d   with  W' = bf16(W diag(gamma)),  c_j = sum_k W'_jk,
+  // d_j = b_j + sum_k beta_k W_jk.  The residual GEMM that produces x also emits what the next GEMM needs:
+  // Producer (in-place residual update, out_f32 == resid, leading dimension N, N % 64 == 0, one batch):
+  //   xb_out    bf16 copy of the updated rows [rows][N]
+  //   stats_out [rows][8] float2 partial (sum, sum of squares) of the updated row; slot = n_tile * 2 + column half
+  //             (256-wide tiles, N = 1024: all 8 slots are written; the consumer adds the 8 slots in order)
+  bf16* xb_out = nullptr;
+  float2* stats_out = nullptr;
+  // Consumer: v = rstd_i * (acc - mean_i * fold_c[j]) + bias[j] before activation / scale; mean / rstd of row i from the
+  // 8 partials of fold_stats (row length fold_len).
+  const float2* fold_stats = nullptr;
+  const float* fold_c = nullptr;
+  int fold_len = 1024;
+  float fold_eps = 1e-5f;
   // Row LayerNorm of the UPDATED fp32 output, fused behind the GEMM (256-wide variants, out_f32 written through TMA
   // store / reduce-add, N <= 1024, N % 128 == 0, one batch): every CTA counts its finished tiles per 128-row block in
   // rowln_counters (zero on entry, left zero on exit); the CTA that adds the last N-tile of a block normalises those rows:

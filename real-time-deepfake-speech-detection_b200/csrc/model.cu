@@ -220,16 +220,43 @@ static int pack_xlsr(rtdf_ctx* c) {
     L.qkv.b = b;
     L.qkv.n = 3072;
     L.qkv.k = 1024;
-    if (bf) {
+    RTDF_TRY(make_ln(c, lp + ".self_attn_layer_norm", 1024, &L.ln1));
+    RTDF_TRY(make_ln(c, lp + ".final_layer_norm", 1024, &L.ln2));
+    RTDF_TRY(make_lin(c, lp + ".self_attn.out_proj", 1024, 1024, true, &L.out));
+    RTDF_TRY(make_lin(c, lp + ".fc2", 1024, 4096, true, &L.fc2));
+    if (bf && !c->ln_fold) {
       RTDF_TRY(to_bf16(c, w, 3072LL * 1024, &L.qkv.wb));
       drop_after_finalize(c, w);
       L.qkv.w = nullptr;
+      RTDF_TRY(make_lin(c, lp + ".fc1", 4096, 1024, true, &L.fc1));
+    } else if (bf) {
+      // RTDF_LN_FOLD=1: the LayerNorm in front of the QKV / fc1 projections is folded into their weights (see run_frontend)
+      auto fold = [&](const float* wf, const float* bias, const Norm& ln, int n, Lin* lin, const float** cv, const float** dv) -> int {
+        bf16* wb;
+        float *cc, *dd;
+        RTDF_TRY(dalloc(c, (long long)n * 1024, &wb));
+        RTDF_TRY(dalloc(c, n, &cc));
+        RTDF_TRY(dalloc(c, n, &dd));
+        RTDF_TRY(fold_ln_weight(0, wf, ln.g, ln.b, bias, n, 1024, wb, cc, dd));
+        lin->wb = wb;
+        lin->w = nullptr;
+        *cv = cc;
+        *dv = dd;
+        return RTDF_OK;
+      };
+      RTDF_TRY(fold(w, b, L.ln1, 3072, &L.qkv, &L.qkv_c, &L.qkv_d));
+      drop_after_finalize(c, w);
+      const float *w1, *b1;
+      RTDF_TRY(get_ptr(c, lp + ".fc1.weight", &w1, 4096LL * 1024));
+      RTDF_TRY(get_ptr(c, lp + ".fc1.bias", &b1, 4096));
+      L.fc1.n = 4096;
+      L.fc1.k = 1024;
+      L.fc1.b = b1;
+      RTDF_TRY(fold(w1, b1, L.ln2, 4096, &L.fc1, &L.fc1_c, &L.fc1_d));
+      drop_after_finalize(c, w1);
+    } else {
+      RTDF_TRY(make_lin(c, lp + ".fc1", 4096, 1024, true, &L.fc1));
     }
-    RTDF_TRY(make_lin(c, lp + ".self_attn.out_proj", 1024, 1024, true, &L.out));
-    RTDF_TRY(make_lin(c, lp + ".fc1", 4096, 1024, true, &L.fc1));
-    RTDF_TRY(make_lin(c, lp + ".fc2", 1024, 4096, true, &L.fc2));
-    RTDF_TRY(make_ln(c, lp + ".self_attn_layer_norm", 1024, &L.ln1));
-    RTDF_TRY(make_ln(c, lp + ".final_layer_norm", 1024, &L.ln2));
   }
   RTDF_TRY(make_ln(c, P + "encoder.layer_norm", 1024, &c->enc_ln));
   return RTDF_OK;
@@ -512,7 +539,7 @@ struct FrontWs {
   void* attn;              // (M,1024)
   void* hbuf;              // (M,4096)
   float* feats;            // (M,1024) fp32
-  int* ln_cnt;             // per 128-row block tile counters of the fused GEMM + LayerNorm (zeroed each forward)
+  float2* stats;           // (M, 8) per-row partial (sum, sum of squares) of the residual stream (folded LayerNorm, bf16 mode)
   float* partials;         // [<= 8][M][1024] K-split partial sums of out_proj / fc2 (streaming-chunk regime only)
   float* gn_ws;            // group-norm extractor mode: conv-0 partial statistics + per-utterance scale / shift
   float* conv_f32;         // (rows, 512) pre-LayerNorm conv output of the short conv layers (streaming-chunk regime only)
@@ -532,7 +559,7 @@ static void plan_front(const rtdf_ctx* c, const Dims& d, bool need_pe, bool own_
   w->attn = b.take<char>((long long)d.M * 1024 * es);
   w->hbuf = b.take<char>((long long)d.M * 4096 * es);
   w->feats = own_feats ? b.take<float>((long long)d.M * 1024) : nullptr;
-  w->ln_cnt = b.take<int>(d.M / 128 + 2);
+  w->stats = b.take<float2>((long long)d.M * 8);
   w->gn_ws = c->fe_group_norm ? b.take<float>((long long)conv0_gn_workspace_floats(d.B, d.N)) : nullptr;
   w->partials = d.M <= kSkinnyRows ? b.take<float>(8LL * d.M * 1024) : nullptr;
   w->conv_f32_rows = d.M <= kSkinnyRows && (long long)d.B * d.L[1] <= kSmallConvRows ? (long long)d.B * d.L[1] : 0;
@@ -677,21 +704,14 @@ static bool conv_2sm_enabled() {
   return v == 1;
 }
 
-static bool fuse_ln_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RTDF_FUSE_LN");
-    v = (e && e[0] == '1') ? 1 : 0;   // opt-in: at B=64 the in-GEMM LayerNorm jobs cost more than the 47 launches they replace
-  }
-  return v == 1;
-}
 
 // y = epilogue(A W^T): dispatch on the context precision
-static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long rows, const Lin& L, const TcEpilogue& e) {
+static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long rows, const Lin& L, const TcEpilogue& e,
+                  bool wide_tiles = false) {
   if (c->d.precision == RTDF_PREC_BF16) {
     int variant = L.n >= 256 ? 256 : (L.n >= 128 ? 128 : 64);
     if (variant == 256 && L.n % 256 == 0 && rows >= 2048 && gemm_2sm_enabled()) variant = 2256;   // CTA-pair tiles
-    if (skinny_rows(c, rows) && L.n % 64 == 0) {
+    if (skinny_rows(c, rows) && L.n % 64 == 0 && !wide_tiles) {
       // Streaming chunks (batch 1-8 x 49 frames, or one 4 s utterance): the GEMM is a weight-streaming problem, so
       // the tile count -- not the tile shape -- sets the time: 64-wide tiles give 4x the CTAs of the 256-wide ones
       // (the residual GEMMs of the transformer layers additionally split K, see run_frontend).
@@ -853,12 +873,15 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     RTDF_CHECK_CUDA(cudaMemcpyAsync(w.xb, w.x, (size_t)M * 1024 * 4, cudaMemcpyDeviceToDevice, s));
     RTDF_TRY(posconv_f32(s, w.x, static_cast<const float*>(w.xb), B, T, c->pos.w, c->pos.b));
   }
-  // transformer layers (pre-LN).  bf16 mode: every LayerNorm that follows a residual GEMM (LN2 after out_proj, the next
-  // layer's LN1 / the final encoder LN after fc2) runs inside that GEMM as soon as a 128-row block is complete.
-  const bool fuse_ln = bf && fuse_ln_enabled();   // opt-in: measured slower both at B=64 and for streaming chunks
+  // transformer layers (pre-LN).  A LayerNorm runs as its own row kernel (at the HBM roofline: 13 us for 12,736 rows).
   // Streaming chunks: out_proj / fc2 (16 output tiles per 128 rows, K up to 4096) split K over the idle SMs; the partial
   // sums land in w.partials and the LayerNorm that follows adds them to x in split order (deterministic).
-  const bool splitk = bf && !fuse_ln && !layer_taps && skinny_rows(c, M) && w.partials;
+  // RTDF_LN_FOLD=1 (bf16, opt-in, measured slower -- profiles/r02_ln_fold_experiment.txt): no LayerNorm kernels at all;
+  // LN(x) W^T + b is evaluated by the projection that follows as rstd_i (bf16(x) W'^T - mean_i c) + d (weights folded at
+  // pack time, gemm_tc.cuh TcEpilogue::fold_*), and the bf16 copy of the residual stream plus the per-row (sum, sum of
+  // squares) come out of the epilogue of the residual GEMM that produced x.
+  const bool fold = bf && c->ln_fold;
+  const bool splitk = bf && !layer_taps && skinny_rows(c, M) && w.partials;
   const int sp_out = splitk ? tc_plan_splits(M, 1024, 1024) : 1, sp_fc2 = splitk ? tc_plan_splits(M, 1024, 4096) : 1;
   int pending = 0;      // K-split partials of the previous residual GEMM not yet folded into x
   auto layer_ln = [&](const Norm& n, float* of32, bf16* ob16) -> int {
@@ -869,27 +892,54 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     }
     return layernorm_rows_f32(s, w.x, M, 1024, n.g, n.b, 1e-5f, ACT_NONE, of32, ob16);
   };
-  auto residual_gemm = [&](const void* A, const Lin& L, int splits, TcEpilogue e) -> int {
+  auto fold_prep = [&]() -> int {          // folded mode: xb / stats for the next projection, if not produced yet
+    if (pending > 1) {
+      const int np = pending;
+      pending = 0;
+      return cast_stats_rows(s, w.x, w.partials, np, M, static_cast<bf16*>(w.xb), w.stats);
+    }
+    return RTDF_OK;
+  };
+  // input of a projection that sits behind a LayerNorm: normalised rows in w.xb, or (folded) the epilogue terms
+  auto ln_input = [&](const Norm& ln, const Lin& L, const float* cvec, const float* dvec, TcEpilogue& e) -> int {
+    if (fold) {
+      RTDF_TRY(fold_prep());
+      e.bias = dvec;
+      e.fold_c = cvec;
+      e.fold_stats = w.stats;
+      return RTDF_OK;
+    }
+    e.bias = L.b;
+    return layer_ln(ln, bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr);
+  };
+  auto residual_gemm = [&](const void* A, const Lin& L, int splits) -> int {   // x += A W^T + b
+    TcEpilogue e;
+    e.bias = L.b;
     if (splits > 1) {
-      TcEpilogue ep;
-      ep.bias = e.bias;
-      ep.partials = w.partials;
+      e.partials = w.partials;
       pending = splits;
-      return tc_gemm(s, plainA(A, M, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, ep);
+      return tc_gemm(s, plainA(A, M, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, e);
+    }
+    e.resid = w.x;
+    e.ldr = 1024;
+    e.out_f32 = w.x;
+    e.ld_f32 = 1024;
+    if (fold) {
+      e.xb_out = static_cast<bf16*>(w.xb);
+      e.stats_out = w.stats;
+      return linear(c, s, A, M, L, e, /*wide_tiles=*/true);
     }
     return linear(c, s, A, M, L, e);
   };
-  if (fuse_ln) RTDF_CHECK_CUDA(cudaMemsetAsync(w.ln_cnt, 0, (size_t)(M / 128 + 2) * sizeof(int), s));
   const size_t n_layers = c->layers.size();
   const size_t tap_bytes = (size_t)M * 1024 * sizeof(float);
   if (layer_taps) RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
+  if (fold) RTDF_TRY(cast_stats_rows(s, w.x, nullptr, 0, M, static_cast<bf16*>(w.xb), w.stats));   // x after the pos-conv
   for (size_t l = 0; l < n_layers; ++l) {
     const XlsrLayer& L = c->layers[l];
-    if (l == 0 || !fuse_ln)
-      RTDF_TRY(layer_ln(L.ln1, bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
     {
       TcEpilogue e;
-      e.bias = L.qkv.b;
+      RTDF_TRY(ln_input(L.ln1, L.qkv, L.qkv_c, L.qkv_d, e));
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.qkv); e.ld_bf16 = 3072; }
       else { e.out_f32 = static_cast<float*>(w.qkv); e.ld_f32 = 3072; }
       RTDF_TRY(linear(c, s, w.xb, M, L.qkv, e));
@@ -906,50 +956,22 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     } else {
       RTDF_TRY(attention_simt_f32(s, static_cast<const float*>(w.qkv), static_cast<float*>(w.attn), B, T, 16));
     }
+    RTDF_TRY(residual_gemm(w.attn, L.out, sp_out));
     {
       TcEpilogue e;
-      e.bias = L.out.b;
-      e.resid = w.x;
-      e.ldr = 1024;
-      e.out_f32 = w.x;
-      e.ld_f32 = 1024;
-      if (fuse_ln) {
-        e.rowln_gamma = L.ln2.g; e.rowln_beta = L.ln2.b; e.rowln_out_bf16 = static_cast<bf16*>(w.xb); e.rowln_counters = w.ln_cnt;
-      }
-      RTDF_TRY(residual_gemm(w.attn, L.out, sp_out, e));
-    }
-    if (!fuse_ln)
-      RTDF_TRY(layer_ln(L.ln2, bf ? nullptr : static_cast<float*>(w.xb), bf ? static_cast<bf16*>(w.xb) : nullptr));
-    {
-      TcEpilogue e;
-      e.bias = L.fc1.b;
       e.act = ACT_GELU;
+      RTDF_TRY(ln_input(L.ln2, L.fc1, L.fc1_c, L.fc1_d, e));
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.hbuf); e.ld_bf16 = 4096; }
       else { e.out_f32 = static_cast<float*>(w.hbuf); e.ld_f32 = 4096; }
       RTDF_TRY(linear(c, s, w.xb, M, L.fc1, e));
     }
-    {
-      TcEpilogue e;
-      e.bias = L.fc2.b;
-      e.resid = w.x;
-      e.ldr = 1024;
-      e.out_f32 = w.x;
-      e.ld_f32 = 1024;
-      if (fuse_ln) {
-        e.rowln_counters = w.ln_cnt;
-        if (l + 1 < n_layers) {
-          e.rowln_gamma = c->layers[l + 1].ln1.g; e.rowln_beta = c->layers[l + 1].ln1.b;
-          e.rowln_out_bf16 = static_cast<bf16*>(w.xb);
-        } else {
-          e.rowln_gamma = c->enc_ln.g; e.rowln_beta = c->enc_ln.b; e.rowln_out_f32 = feats;
-        }
-      }
-      RTDF_TRY(residual_gemm(w.hbuf, L.fc2, sp_fc2, e));
-    }
-    if (layer_taps)   // output of encoder.layers[l] (the KD hook point, trainer.py:176-195)
+    RTDF_TRY(residual_gemm(w.hbuf, L.fc2, sp_fc2));
+    if (layer_taps) {  // output of encoder.layers[l] (the KD hook point, trainer.py:176-195)
+      if (fold) RTDF_TRY(fold_prep());
       RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps + (l + 1) * (size_t)M * 1024, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
+    }
   }
-  if (!fuse_ln) RTDF_TRY(layer_ln(c->enc_ln, feats, nullptr));
+  RTDF_TRY(layer_ln(c->enc_ln, feats, nullptr));
   return RTDF_OK;
 }
 
@@ -1326,6 +1348,10 @@ int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc) {
   if (c->d.conf_heads == 0) c->d.conf_heads = 4;
   if (c->d.conf_kernel == 0) c->d.conf_kernel = 31;
   if (c->d.conf_blocks == 0) c->d.conf_blocks = 4;
+  {
+    const char* e = getenv("RTDF_LN_FOLD");
+    c->ln_fold = e && e[0] == '1' && c->d.precision == RTDF_PREC_BF16;
+  }
   {  // second stream + fork / join events for the independent graph branches of the AASIST back-end (RTDF_BRANCH_STREAMS=0: off)
     const char* e = getenv("RTDF_BRANCH_STREAMS");
     if (!(e && e[0] == '0') && c->d.backend == RTDF_BACKEND_AASIST) {

@@ -38,6 +38,10 @@ struct FeConv {
 struct XlsrLayer {
   Lin qkv, out, fc1, fc2;
   Norm ln1, ln2;
+  // RTDF_LN_FOLD=1 (bf16): qkv.wb / fc1.wb hold W' = bf16(W diag(gamma)) of the LayerNorm in front of them; c = column sums of W',
+  // d = bias + W beta (folded LayerNorm, gemm_tc.cuh TcEpilogue::fold_*)
+  const float* qkv_c = nullptr; const float* qkv_d = nullptr;
+  const float* fc1_c = nullptr; const float* fc1_d = nullptr;
 };
 
 struct TcConvW {      // weights of one shifted-row tcgen05 conv: [n_chunks][co][min(ci,64)] bf16 (hi, lo)
@@ -108,6 +112,7 @@ struct rtdf_ctx {
   int device = 0;
   rtdf_model_desc d{};
   bool finalized = false;
+  bool ln_fold = false;            // RTDF_LN_FOLD=1 (bf16): LayerNorms folded into the neighbouring GEMMs (opt-in experiment)
   int regime = RTDF_REGIME_AUTO;   // rtdf_set_regime
   cudaStream_t side_stream = nullptr;   // AASIST back-end: second stream for the independent graph branches
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -62,6 +62,11 @@ SIGNATURES = {
     "rtdf_gemm_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "rtdf_gemm_bf16_rowln": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rtdf_fold_ln_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rtdf_gemm_bf16_xres": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "rtdf_cast_stats_rows": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),
+    "rtdf_gemm_bf16_lnfold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p]),
     "rtdf_gemm_plan_splits": (c_int, [c_int, c_int, c_int]),
     "rtdf_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rtdf_layernorm_accum_rows": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_float, c_void_p,

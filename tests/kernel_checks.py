@@ -298,6 +298,75 @@ def check_gemm_rowln(variants=(256, 2256)):
     return out
 
 
+def check_gemm_lnfold(variants=(256, 2256)):
+    """LayerNorm folded into the GEMMs around it (how the bf16 transformer layers run): the residual GEMM emits x, bf16(x)
+    and per-row partial statistics; the next projection evaluates LN(x) W^T + b as rstd (bf16(x) W'^T - mean c) + d."""
+    g = torch.Generator().manual_seed(17)
+    out = {}
+    N = 1024
+    for M, K, N2 in ((12736, 1024, 3072), (300, 4096, 4096), (49, 1024, 1024), (2500, 256, 512)):
+        A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, generator=g)
+        x0 = torch.randn(M, N, generator=g) * 2 + 0.3
+        gamma = 1 + 0.1 * torch.randn(N, generator=g)
+        beta = 0.1 * torch.randn(N, generator=g)
+        W2 = torch.randn(N2, N, generator=g) / math.sqrt(N)
+        b2 = torch.randn(N2, generator=g)
+        xr = x0 + A.float() @ W.float().t() + b
+        ref = F.gelu(F.layer_norm(xr, (N,), gamma, beta, 1e-5) @ W2.t() + b2)
+        wf = torch.empty(N2, N, dtype=torch.bfloat16, device=DEV)
+        cv, dv = torch.empty(N2, device=DEV), torch.empty(N2, device=DEV)
+        call("rtdf_fold_ln_weight", P(dev(W2)), P(dev(gamma)), P(dev(beta)), P(dev(b2)), N2, N, P(wf), P(cv), P(dv), stream())
+        want_wf = (W2 * gamma).to(torch.bfloat16)
+        assert torch.equal(wf.cpu(), want_wf), "folded weight"
+        assert float((cv.cpu() - want_wf.float().sum(1)).abs().max()) <= 1e-3
+        assert float((dv.cpu() - (b2 + W2 @ beta)).abs().max()) <= 1e-4
+        Ad, Wd, bd = dev(A), dev(W), dev(b)
+        for v in variants:
+            runs = []
+            for rep in range(2):
+                x = x0.to(DEV)
+                xb = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+                stats = torch.full((M, 8, 2), float("nan"), device=DEV)
+                call("rtdf_gemm_bf16_xres", P(Ad), P(Wd), M, N, K, P(bd), P(x), P(xb), P(stats), v, stream())
+                o16 = torch.zeros(M, N2, dtype=torch.bfloat16, device=DEV)
+                call("rtdf_gemm_bf16_lnfold", P(xb), P(wf), M, N2, N, P(cv), P(dv), P(stats), 1e-5, 1, None, P(o16),
+                     v, stream())
+                runs.append((x.cpu(), xb.cpu(), stats.cpu(), o16.cpu()))
+            x, xb, stats, o16 = runs[0]
+            dx = float((x - xr).abs().max())
+            assert dx <= 2e-3, (M, K, v, dx)                        # fp32 accumulation order only
+            assert torch.equal(xb, x.to(torch.bfloat16)), "bf16 copy of the residual stream"
+            ssum, ssq = stats[:, :, 0].sum(1), stats[:, :, 1].sum(1)
+            assert float((ssum - x.sum(1)).abs().max()) <= 2e-2 and float((ssq / x.pow(2).sum(1) - 1).abs().max()) <= 1e-4
+            d16 = float((o16.float() - ref).abs().max())
+            out[f"{M}x{K}->{N2}_v{v}"] = (dx, d16)
+            assert d16 <= 0.06, out              # bf16 rounding of x, of W' and of the O(4) outputs
+            for a_, b_ in zip(runs[0], runs[1]):     # no atomics anywhere: bit-reproducible
+                assert torch.equal(a_, b_) or (torch.isnan(a_) == torch.isnan(b_)).all()
+        # streaming-chunk producer: K-split partial sums folded by the cast kernel, consumer on 64-wide tiles (direct stores)
+        if M <= 512:
+            from tests.util import native
+            lib = native().load()
+            S = lib.rtdf_gemm_plan_splits(M, N, K)
+            parts = torch.empty(S, M, N, device=DEV)
+            call("rtdf_gemm_bf16_splitk", P(Ad), P(Wd), M, N, K, P(bd), P(parts), stream())
+            x = x0.to(DEV)
+            xb = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+            stats = torch.full((M, 8, 2), float("nan"), device=DEV)
+            call("rtdf_cast_stats_rows", P(x), P(parts), S, M, P(xb), P(stats), stream())
+            assert float((x.cpu() - xr).abs().max()) <= 2e-3
+            assert torch.equal(xb.cpu(), x.cpu().to(torch.bfloat16))
+            assert float(stats[:, 1:, :].abs().max()) == 0.0
+            o16 = torch.zeros(M, N2, dtype=torch.bfloat16, device=DEV)
+            call("rtdf_gemm_bf16_lnfold", P(xb), P(wf), M, N2, N, P(cv), P(dv), P(stats), 1e-5, 1, None, P(o16), 64, stream())
+            d16 = float((o16.float().cpu() - ref).abs().max())
+            out[f"{M}x{K}->{N2}_skinny"] = d16
+            assert d16 <= 0.06, out
+    return out
+
+
 def check_gelu_epilogue():
     """The tensor-core epilogue GELUs against the exact erf GELU on a dense grid (identity GEMM, fp32 output).
     act 1 = sigmoid-of-quintic fit (product default), 4 = hardware-tanh form, 5 = A&S 7.1.26 erf."""

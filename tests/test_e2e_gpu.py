@@ -53,6 +53,24 @@ def test_timed_configuration_parity_and_batch_invariance():
     ec.check_timed_configuration()
 
 
+def test_folded_layernorm_mode(monkeypatch):
+    """RTDF_LN_FOLD=1 (opt-in): no LayerNorm kernels in the transformer layers -- the projections apply the normalisation
+    in their epilogues from per-row statistics the residual GEMMs emit.  Same tolerances as the default path, in the
+    streaming-chunk regime (K-split partials + cast kernel), on the wide tiles and through the KD layer taps."""
+    import torch
+    from tests.util import build_pair
+    monkeypatch.setenv("RTDF_LN_FOLD", "1")
+    ec.check_e2e(kind="My_XLSR_AASIST", precision="bf16", B=2, N=16000, num_layers=3, order="first")     # 98 rows: split-K
+    ec.check_e2e(kind="My_XLSR_AASIST", precision="bf16", B=4, N=64000, num_layers=3, order="first")     # 796 rows: 256-wide tiles
+    ora, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=2, order="first")
+    x = ec._waves(2, 16000, seed=3)
+    _, taps = prod.engine().forward(x.cuda(), want_taps=True, layer_taps=True)
+    with torch.no_grad():
+        ref = ora.ssl_model.extract_feat(x)
+    assert float((taps["feats"].cpu() - ref).abs().max()) <= ec.FEATS_TOL["bf16"]
+    assert taps["layers"].shape == (3, 2, 49, 1024)
+
+
 def test_ragged_batches_preemphasis_determinism():
     ec.check_ragged_and_quirks(precision="fp32")
 

@@ -58,6 +58,11 @@ def test_gemm_with_fused_row_layernorm(variant):
     kc.check_gemm_rowln(variants=(variant,))
 
 
+@pytest.mark.parametrize("variant", [256, 2256])
+def test_gemm_with_folded_layernorm(variant):
+    kc.check_gemm_lnfold(variants=(variant,))
+
+
 def test_gelu_epilogue_accuracy():
     kc.check_gelu_epilogue()
 

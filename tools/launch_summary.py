@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals of ONE forward
-(the launches between two conv0 kernels).  python tools/launch_summary.py launches.csv [forward_index]"""
+(the launches between two conv-0 kernels: conv0_kernel | conv0_im2col_kernel | conv0_gn_stats_kernel).  python tools/launch_summary.py launches.csv [forward_index]"""
 import collections
 import csv
 import re
@@ -12,7 +12,7 @@ def main():
     with open(path) as f:
         lines = [l for l in f if l.startswith('"')]
     rows = [(r["Kernel Name"], float(r["Metric Value"]) / 1000, r["Grid Size"]) for r in csv.DictReader(lines)]
-    idx = [i for i, (k, _, _) in enumerate(rows) if "conv0_kernel" in k]
+    idx = [i for i, (k, _, _) in enumerate(rows) if "conv0_kernel" in k or "conv0_im2col" in k or "conv0_gn_stats" in k]
     lo = idx[which]
     hi = idx[which + 1] if which + 1 < len(idx) else len(rows)
     fw = rows[lo:hi]

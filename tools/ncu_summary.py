@@ -7,10 +7,11 @@ COLS = [
     ("gpu__time_duration.sum", "us", 1e-3),
     ("dram__bytes_read.sum", "rdMB", None),
     ("dram__bytes_write.sum", "wrMB", None),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%", 1),
+    (("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed"), "dram%", 1),
     ("lts__t_sector_hit_rate.pct", "L2hit%", 1),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%", 1),
-    ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor%", 1),
+    (("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"), "tensor%", 1),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%", 1),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%", 1),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%", 1),
@@ -37,6 +38,8 @@ def main():
             name = name.replace("void ", "").replace("rtdf::", "").replace("<unnamed>::", "").split("(")[0][:43]
             out = []
             for key, label, scale in COLS:
+                if isinstance(key, tuple):     # first spelling of the metric this ncu version exported
+                    key = next((k for k in key if k in idx), key[0])
                 if key not in idx or r[idx[key]] == "":
                     out.append("-".rjust(8))
                     continue

@@ -33,6 +33,8 @@ struct KParams {
   float* out_f32;
   bf16* out_hi;
   bf16* out_lo;
+  int debug;     // RTDF_CONVTC_DEBUG bit mask -- timing experiments only (wrong results): 1 = no residual loads, 2 = no fp32 store,
+                 // 4 = no hi / lo stores, 8 = no MMAs, 16 = no slab loads
 };
 
 __device__ __forceinline__ float selu_fast(float x) {
@@ -91,7 +93,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), kEpiThreads / 32);   // one elected arrive per epilogue warp (256 per-thread arrives on one
+                                                     // shared-memory word serialise: ~1 us per tile)
     }
     fence_mbar_init();
   }
@@ -125,6 +128,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const int s = it % p.n_stages;
         const uint32_t ph = (it / p.n_stages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
+        if (p.debug & 16) {
+          mbar_arrive(full_bar(s));
+          continue;
+        }
         mbar_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = smem_base + off_stages + s * stage_bytes;
         const int row0 = t * kTileM + p.shift_min;        // may be negative / run past the end: TMA zero-fills
@@ -153,7 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const uint32_t a_hi = smem_base + off_stages + s * stage_bytes;
         const uint32_t a_lo = a_hi + a_half_bytes;
         uint32_t first = 1;
-        for (int c = 0; c < p.n_chunks; ++c) {
+        for (int c = 0; c < p.n_chunks && !(p.debug & 8); ++c) {
           const uint32_t ah = a_hi + p.a_off[c], al = a_lo + p.a_off[c];
           const uint32_t wh = smem_base + c * kWChunkBytes, wl = wh + w_half_bytes;
 #pragma unroll
@@ -192,23 +199,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
       const int wp = (int)(m % p.Wp);
       const int hp = (int)((m / p.Wp) % p.Hp);
       const bool ok = in_range && wp >= 1 && wp <= p.Wp - 2 && hp >= p.hp_lo && hp <= p.hp_hi;
+      // the residual does not depend on this tile's MMAs: its loads are in flight while the accumulator is awaited
+      constexpr int kChunks = CO / 32;              // 16-column chunks per thread (this warp's half of the CO columns)
+      float4 rs[kChunks][4];
+      if (p.resid && ok && !(p.debug & 1)) {
+        const float4* rp = reinterpret_cast<const float4*>(p.resid + m * CO + c_begin);
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs[ch][j] = rp[ch * 4 + j];
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rs[ch][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(tfull_bar(a), aph);
       __syncwarp();
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * CO;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 16) {
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const int c = c_begin + ch * 16;
         uint32_t r[16];
         tmem_ld16(t_row + c, r);
-        float4 rs[4];
-        if (p.resid && ok) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + m * CO + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rs[j] = rp[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         tmem_ld_wait();
         float v[16];
 #pragma unroll
@@ -216,18 +230,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
           float x = __uint_as_float(r[i]) + s_bias[c + i];
           if (has1) x = fmaf(x, s_s1[c + i], s_t1[c + i]);
           if (p.act1 == ACT_SELU) x = selu_fast(x);
-          x += reinterpret_cast<const float*>(rs)[i];
+          x += reinterpret_cast<const float*>(rs[ch])[i];
           if (has2) x = fmaf(x, s_s2[c + i], s_t2[c + i]);
           if (p.act2 == ACT_SELU) x = selu_fast(x);
           v[i] = ok ? x : 0.f;
         }
         if (in_range) {
-          if (p.out_f32) {
+          if (p.out_f32 && !(p.debug & 2)) {
             float4* o = reinterpret_cast<float4*>(p.out_f32 + m * CO + c);
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (p.out_hi) {
+          if (p.out_hi && !(p.debug & 4)) {
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -247,7 +261,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(a));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));
     }
   }
   tc_fence_before();
@@ -292,6 +307,14 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
   p.total_tiles = (int)tiles;
   p.hp_lo = a.hp_lo;
   p.hp_hi = a.hp_hi;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("RTDF_CONVTC_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.bias = a.bias; p.s1 = a.s1; p.t1 = a.t1; p.act1 = a.act1; p.resid = a.resid;
   p.s2 = a.s2; p.t2 = a.t2; p.act2 = a.act2;
   p.out_f32 = a.out_f32; p.out_hi = a.out_hi; p.out_lo = a.out_lo;

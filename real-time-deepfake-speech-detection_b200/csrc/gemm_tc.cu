@@ -462,7 +462,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), Cfg::kEpiWarps);   // one elected arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -674,7 +674,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       // all TMEM reads of this stage are complete (tmem_ld_wait above): hand the stage back to the MMA warp
       tc_fence_before();
-      mbar_arrive(tempty_bar(a));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));
       if (!kLN && p.epi.rowln_counters)
         rowln_after_tile<kEpiThreads>(p, m_tile, m0, et, lane, reinterpret_cast<volatile int*>(smem_gen + kOffBars + 240));
     }

@@ -72,7 +72,7 @@ posconv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       mbar_init(slab_full(i), 1);
       mbar_init(slab_empty(i), 1);
       mbar_init(tfull(i), 1);
-      mbar_init(tempty(i), kEpiThreads);
+      mbar_init(tempty(i), kEpiThreads / 32);   // one elected arrive per epilogue warp
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(w_full(s), 1);
@@ -210,7 +210,8 @@ posconv_slab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty(a));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(a));
     }
   }
   tc_fence_before();

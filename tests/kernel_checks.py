@@ -24,6 +24,27 @@ def dev(t):
 
 
 
+class Guarded:
+    """Output buffer with canary margins (compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are caught
+    here): the kernel gets a view into the middle of a larger allocation; check() asserts the margins are untouched."""
+    PAD = 4096          # elements on either side
+    CANARY = -7777.0
+
+    def __init__(self, shape, dtype=torch.float32, fill=0.0):
+        n = 1
+        for d in shape:
+            n *= d
+        self.raw = torch.full((n + 2 * self.PAD,), self.CANARY, dtype=dtype, device=DEV)
+        self.t = self.raw[self.PAD:self.PAD + n].view(*shape)
+        self.t.fill_(fill)
+
+    def check(self, what=""):
+        lo, hi = self.raw[:self.PAD], self.raw[-self.PAD:]
+        ok = bool((lo == self.CANARY).all()) and bool((hi == self.CANARY).all())
+        assert ok, f"out-of-bounds write next to the output of {what}"
+        return self.t
+
+
 def _rel(a, b):
     return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
 
@@ -131,9 +152,11 @@ def check_conv0_tc(shapes=((2, 16000), (1, 4003), (3, 64600))):
             ref = F.gelu(F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5))
         L = ref.shape[1]
         scratch = torch.empty(int(lib.rtdf_conv0_tc_scratch_bytes(B, N)), dtype=torch.uint8, device=DEV)
-        o16 = torch.zeros(B, L, 512, dtype=torch.bfloat16, device=DEV)
+        go = Guarded((B, L, 512), torch.bfloat16)
+        o16 = go.t
         call("rtdf_conv0_tc_ln_gelu", P(dev(wav)), B, N, P(dev(w.reshape(512, 10).contiguous())), P(dev(b)), P(dev(gamma)),
              P(dev(beta)), 1e-5, P(scratch), P(o16), stream())
+        go.check(f"rtdf_conv0_tc_ln_gelu {B}x{N}")
         got = o16.float().cpu()
         d16 = float((got - ref).abs().max())
         # the SIMT kernel's bf16 output of the same layer: both round the same fp32 value, so they agree to one bf16 ulp
@@ -504,9 +527,11 @@ def check_conv1d_tc(variants=(512, 513), shapes=CONV1D_SHAPES):
         Lo = ref.shape[1]
         wp = w.permute(0, 2, 1).contiguous().to(DEV)               # [co][k][ci]
         for v in variants:
-            y = torch.zeros(B, Lo, 512, dtype=torch.bfloat16, device=DEV)
+            gy = Guarded((B, Lo, 512), torch.bfloat16)
+            y = gy.t
             call("rtdf_conv1d_ln_gelu_bf16", P(dev(x)), B, L, k, 2, P(wp), P(dev(b)), P(dev(gamma)),
                  P(dev(beta)), 1e-5, P(y), v, stream())
+            gy.check(f"rtdf_conv1d_ln_gelu_bf16 variant {v} B{B} L{L}")
             d = float((y.float().cpu() - ref).abs().max())
             out[f"B{B}_L{L}_k{k}_v{v}"] = d
             assert d <= 0.04, out    # bf16 output rounding of O(4) values
@@ -543,8 +568,11 @@ def check_posconv(shapes=POSCONV_SHAPES):
         ref16 = x + (_posconv_ref(xb.float(), wb.float().reshape(1024, 128, 64).permute(0, 2, 1), bias) - xb.float())
         d16 = 0.0
         for impl in (0, 1):      # 0 = slab-resident kernel, 1 = tap-shifted GEMM
-            xo2 = x.clone().to(DEV)
+            gx = Guarded((B, T, 1024))
+            xo2 = gx.t
+            xo2.copy_(x)
             call("rtdf_posconv_bf16", P(xo2), P(dev(xb)), B, T, P(dev(wb)), P(dev(bias)), impl, stream())
+            gx.check(f"rtdf_posconv_bf16 impl {impl} B{B} T{T}")
             d16 = max(d16, float((xo2.cpu() - ref16).abs().max()))
         out[f"B{B}_T{T}"] = (d32, d16)
         assert d32 <= 5e-5, out
@@ -583,8 +611,10 @@ def check_attention(impls=(0, 1), shapes=ATTN_SHAPES):
         qb = qkv.to(torch.bfloat16)
         ref16 = _attn_ref(qb, B, T, H)
         for impl in impls:
-            o16 = torch.zeros(B * T, H * 64, dtype=torch.bfloat16, device=DEV)
+            go = Guarded((B * T, H * 64), torch.bfloat16)
+            o16 = go.t
             call("rtdf_attention", P(dev(qb)), P(o16), B, T, H, 1, impl, stream())
+            go.check(f"rtdf_attention impl {impl} B{B} T{T} H{H}")
             d = float((o16.float().cpu() - ref16).abs().max())
             out[f"B{B}_T{T}_H{H}_bf16_impl{impl}"] = d
             assert d <= 0.03, out     # bf16 P and bf16 output rounding, |out| <~ 3

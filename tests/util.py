@@ -42,9 +42,17 @@ def gemm_bf16(A, W, bias=None, act=0, scale=1.0, resid=None, out="f32", variant=
         x = resid.clone()
         call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, scale, P(x), P(x), None, variant, stream())
         return x
-    o32 = torch.empty(M, N, dtype=torch.float32, device=A.device) if out in ("f32", "both") else None
-    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=A.device) if out in ("bf16", "both") else None
+    # canary margins around the outputs: an out-of-bounds write of a tile epilogue / TMA store fails the check
+    pad, canary = 4096, -7777.0
+    raw32 = torch.full((M * N + 2 * pad,), canary, dtype=torch.float32, device=A.device) if out in ("f32", "both") else None
+    raw16 = torch.full((M * N + 2 * pad,), canary, dtype=torch.bfloat16, device=A.device) if out in ("bf16", "both") else None
+    o32 = raw32[pad:pad + M * N].view(M, N) if raw32 is not None else None
+    o16 = raw16[pad:pad + M * N].view(M, N) if raw16 is not None else None
     call("rtdf_gemm_bf16", P(A), P(W), M, N, K, P(bias), act, scale, P(resid), P(o32), P(o16), variant, stream())
+    for raw in (raw32, raw16):
+        if raw is not None:
+            assert bool((raw[:pad] == canary).all()) and bool((raw[-pad:] == canary).all()), \
+                f"rtdf_gemm_bf16 variant {variant} ({M},{N},{K}) wrote outside its output"
     return o32 if out == "f32" else (o16 if out == "bf16" else (o32, o16))
 
 

@@ -1355,9 +1355,14 @@ int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc) {
   {  // second stream + fork / join events for the independent graph branches of the AASIST back-end (RTDF_BRANCH_STREAMS=0: off)
     const char* e = getenv("RTDF_BRANCH_STREAMS");
     if (!(e && e[0] == '0') && c->d.backend == RTDF_BACKEND_AASIST) {
-      RTDF_CHECK_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-      RTDF_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-      RTDF_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+      cudaError_t err = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+      if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+      if (err != cudaSuccess) {
+        rtdf::set_error("rtdf_create: cannot create the branch stream / events: %s", cudaGetErrorString(err));
+        rtdf_destroy(c);
+        return RTDF_ERR_CUDA;
+      }
     }
   }
   *out = c;

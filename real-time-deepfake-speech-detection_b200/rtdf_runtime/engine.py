@@ -120,14 +120,16 @@ class Engine:
                                            native.ptr(logits), native.ptr(ws), ws.numel(), None,
                                            ctypes.c_void_p(stream)), "rtdf_forward")
 
-    def _graph_forward(self, wav, B, N, preemph, coef, regime):
+    def _graph_entry(self, B, N, preemph, coef, regime, first_input=None):
+        """(graph, static_in, static_out) for one input shape; captured on first use."""
         key = (B, N, bool(preemph), float(coef), regime)
         ws = self._workspace(B, N)
         entry = self._graphs.get(key)
         if entry is None:
-            static_in = torch.empty(B, N, dtype=torch.float32, device=self.device)
+            static_in = torch.zeros(B, N, dtype=torch.float32, device=self.device)
             static_out = torch.empty(B, 2, dtype=torch.float32, device=self.device)
-            static_in.copy_(wav)
+            if first_input is not None:
+                static_in.copy_(first_input)
             self._launch_forward(static_in, B, N, preemph, coef, static_out, ws)   # eager warm-up (also validates)
             torch.cuda.current_stream(self.device).synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -136,10 +138,31 @@ class Engine:
             if len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
             entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
-        static_in.copy_(wav)
+        return entry
+
+    def _graph_forward(self, wav, B, N, preemph, coef, regime):
+        graph, static_in, static_out = self._graph_entry(B, N, preemph, coef, regime, first_input=wav)
+        if wav.data_ptr() != static_in.data_ptr():      # zero-copy when the caller filled static_input() directly
+            static_in.copy_(wav)
         graph.replay()
         return static_out.clone()
+
+    def static_input(self, B, N, preemph=False, coef=0.97, regime=None):
+        """The (B,N) fp32 device buffer the captured graph of this shape reads.  A streaming caller copies its chunk
+        straight into it (e.g. ``buf.copy_(pinned_host, non_blocking=True)``) and passes it to ``forward`` /
+        ``forward_static``: no device-to-device staging copy on the latency path."""
+        with torch.cuda.device(self.device):
+            regime = self._apply_regime(regime)
+            return self._graph_entry(int(B), int(N), preemph, coef, regime)[1]
+
+    def forward_static(self, B, N, preemph=False, coef=0.97, regime=None):
+        """Replay the captured graph on whatever ``static_input(B, N)`` holds; returns the graph's own (B,2) output buffer
+        (valid until the next replay of this shape).  Two launches fewer than ``forward`` per call."""
+        with torch.cuda.device(self.device):
+            regime = self._apply_regime(regime)
+            graph, _, static_out = self._graph_entry(int(B), int(N), preemph, coef, regime)
+            graph.replay()
+        return static_out
 
     def _check_wav(self, wav):
         if not torch.is_tensor(wav) or not wav.is_cuda:

@@ -183,3 +183,19 @@ def test_scoring_pipeline_matches_direct_forward_bit_exactly():
     pool = x.pin_memory()
     zero_copy = scoring.score_utterances(prod, 11, lambda lo, hi, out: pool[lo:hi], N, 3, "cuda")   # other batch size
     assert torch.equal(zero_copy.cpu(), want)
+
+
+def test_streaming_static_buffers_match_forward():
+    """Engine.static_input / forward_static (zero-copy streaming calls) give the scores of Engine.forward bit for bit."""
+    from oracle import models_ref as O
+    _, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=1, order="first")
+    eng = prod.engine()
+    x = O.synth_waveforms(3, 16000, seed=9)
+    want = [eng.forward(x[i:i + 1].cuda()).cpu() for i in range(3)]
+    buf = eng.static_input(1, 16000)
+    host = x.pin_memory()
+    for i in range(3):
+        buf.copy_(host[i:i + 1], non_blocking=True)
+        got = eng.forward_static(1, 16000).cpu()
+        assert torch.equal(got, want[i]), i
+    assert torch.equal(eng.forward(buf).cpu(), want[2])       # the static buffer itself is accepted without a copy

@@ -278,6 +278,33 @@ def latency_config(torch, model, n_samples, batch, device, n_warm, n_calls, hbm_
                       "+ D2H of the score + sync"}
 
 
+def cublas_same_state(torch, device, M):
+    """cuBLAS (torch.matmul, bf16) on the four projection shapes of one transformer layer, timed with CUDA events in the
+    thermal / clock state the roofline leg ran in: the library comparator for `roofline.achieved` (a measurement
+    reference only -- nothing of it is on the product path)."""
+    shapes = ((3072, 1024), (1024, 1024), (4096, 1024), (1024, 4096))
+    ops = []
+    for n, k in shapes:
+        a = torch.randn(M, k, device=device).to(torch.bfloat16)
+        w = torch.randn(n, k, device=device).to(torch.bfloat16)
+        ops.append((a, w.t()))
+    for a, wt in ops:
+        torch.matmul(a, wt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    e0.record()
+    for _ in range(reps):
+        for a, wt in ops:
+            torch.matmul(a, wt)
+    e1.record()
+    torch.cuda.synchronize()
+    flops = reps * sum(2.0 * M * n * k for n, k in shapes)
+    tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return {"tflops": tf, "how": f"torch.matmul bf16, M = {M}, (N,K) = {list(shapes)}, {reps} rounds back to back, no epilogue "
+                                 "(our launches carry bias / GELU / residual epilogues)"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -387,6 +414,41 @@ def run_b200(args):
     assert bool(torch.isfinite(all_scores).all()), "non-finite scores"
     timed_logits_first = eng.forward(inputs[0]).clone()       # same graph replay as timed step 0 (deterministic)
 
+    # ---- roofline leg, right behind the timed region (same clocks / temperature): CUDA-event time of every launch of
+    # ---- the dominant kernel inside real (non-graph) steps, and cuBLAS on the same four GEMM shapes as the comparator
+    roofline = None
+    if rank == 0:
+        eng.use_graph = False                      # per-launch events need real launches, not a graph replay
+        native.check(lib.rtdf_profile_begin(), "rtdf_profile_begin")
+        n_prof = 3
+        for i in range(n_prof):
+            eng.forward(inputs[i % n_bufs])
+        torch.cuda.synchronize()
+        eng.use_graph = graph_on
+        pms, pfl, pn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        native.check(lib.rtdf_profile_end(256, ctypes.byref(pms), ctypes.byref(pfl), ctypes.byref(pn)), "rtdf_profile_end")
+        peaks = measured_peaks()
+        traffic, traffic_src = None, None
+        for name in ("r02_traffic.json", "r01_traffic.json"):         # from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get("dram_bytes_per_launch")
+                traffic_src = f"DRAM bytes per launch (ncu, profiles/{name})"
+                break
+        if pn.value > 0 and pms.value > 0:
+            achieved = pfl.value / (pms.value * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM, 256-wide tiles: tc_gemm_2sm_kernel (CTA pair) / tc_gemm_kernel<256,64> (QKV/out/FFN projections)",
+                        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
+                        "traffic": traffic, "traffic_unit": traffic_src,
+                        "launches_timed": pn.value, "avg_launch_ms": pms.value / pn.value,
+                        "flops_per_launch_avg": pfl.value / pn.value, "peak_source": peaks["source"] + ", sustained",
+                        "share_of_step": (pms.value / n_prof) / (ms / K),
+                        "whole_path_frac": value * GFLOP_PER_UTT * 1e9 / world / 1e12 / peaks["bf16_sustained"],
+                        "cublas_same_state": cublas_same_state(torch, device, B * eng.num_frames(N))}
+            roofline["frac_of_cublas_same_state"] = achieved / roofline["cublas_same_state"]["tflops"]
+
     # ---- end-to-end through the package's scoring API (pinned HOST input -> HOST scores) -----------
     # Every step: H2D of that step's batch from pinned host memory (side stream), forward, D2H of its scores.
     host = [inputs[i].cpu().pin_memory() for i in range(n_bufs)]
@@ -452,37 +514,6 @@ def run_b200(args):
                  "api": "scoring.score_utterances (ScoringPipeline per rank, throughput regime, one all_gather_into_tensor); "
                         "utterance i = f(SWEEP_SEED + i) only, so the digest must be equal at N = 1/2/4/8"}
         del pool
-
-    # ---- roofline leg: CUDA-event time of every launch of the dominant kernel inside real steps ---
-    roofline = None
-    if rank == 0:
-        eng.use_graph = False                      # per-launch events need real launches, not a graph replay
-        native.check(lib.rtdf_profile_begin(), "rtdf_profile_begin")
-        for i in range(2):
-            eng.forward(inputs[i % n_bufs])
-        torch.cuda.synchronize()
-        eng.use_graph = graph_on
-        pms, pfl, pn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
-        native.check(lib.rtdf_profile_end(256, ctypes.byref(pms), ctypes.byref(pfl), ctypes.byref(pn)), "rtdf_profile_end")
-        peaks = measured_peaks()
-        traffic, traffic_src = None, None
-        for name in ("r02_traffic.json", "r01_traffic.json"):         # from the committed ncu --set full capture
-            tpath = os.path.join(ROOT, "profiles", name)
-            if os.path.exists(tpath):
-                with open(tpath) as fh:
-                    traffic = json.load(fh).get("dram_bytes_per_launch")
-                traffic_src = f"DRAM bytes per launch (ncu, profiles/{name})"
-                break
-        if pn.value > 0 and pms.value > 0:
-            achieved = pfl.value / (pms.value * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM, 256-wide tiles: tc_gemm_2sm_kernel (CTA pair) / tc_gemm_kernel<256,64> (QKV/out/FFN projections)",
-                        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["bf16_sustained"], "frac_of_burst": achieved / peaks["bf16_burst"],
-                        "traffic": traffic, "traffic_unit": traffic_src,
-                        "launches_timed": pn.value, "avg_launch_ms": pms.value / pn.value,
-                        "flops_per_launch_avg": pfl.value / pn.value, "peak_source": peaks["source"] + ", sustained",
-                        "share_of_step": (pms.value / 2) / (ms / K),
-                        "whole_path_frac": value * GFLOP_PER_UTT * 1e9 / world / 1e12 / peaks["bf16_sustained"]}
 
     # ---- parity of the timed batch against the CPU oracle (rank 0, outside every timed region) -------------------
     parity = None

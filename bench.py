@@ -13,6 +13,7 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
   sweep     BASELINE.json configs[3] in small: a fixed set of 8,229 utterances seeded by GLOBAL index, sharded over
             the ranks through scoring.score_utterances (ragged tail, one all-gather); sha256 of the gathered fp32
             score vector -- identical at N = 1/2/4/8
+  secondary BASELINE.json configs[1]: distilled student (6 layers) AASIST / Conformer at batch 256, utt/s (N = 1 only)
   latency   BASELINE.json configs[4]: p50 / p99 ms of single streaming-chunk calls (pinned host waveform -> host
             score), XLSR-AASIST 1 s and 4 s, Conformer 1 s, batch 1 (N = 1 only)
   roofline  dominant kernel (tcgen05 GEMM, 256-wide tiles): algorithmic FLOPs / CUDA-event time, vs the
@@ -58,6 +59,7 @@ def parse():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--sweep-utterances", type=int, default=SWEEP_UTTERANCES)
     ap.add_argument("--latency-calls", type=int, default=1000)
     ap.add_argument("--warm-seconds", type=float, default=1.0,
@@ -550,6 +552,40 @@ def run_b200(args):
         latency["conformer_b1_1s"] = latency_config(torch, conf, 16000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], 636e6)
         del conf
 
+    # ---- BASELINE.json configs[1]: distilled student (6 of 24 layers), batch 256, 4 s (rank 0, N = 1 only) -------------
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary and args.layers == 24:
+        del model, eng
+        torch.cuda.empty_cache()
+        secondary = {}
+        cb = importlib.import_module(PKG + ".models.conformer_baseline")
+        for name, build, gflop in (
+                ("student6_aasist_b256", lambda: xa.My_XLSR_AASIST("cpu", None, num_layers=6, order="first"), 55.59),
+                ("student6_conformer_b256", lambda: cb.MyModel("cpu", None, fixed_call=True, num_layers=6), 55.27)):
+            torch.manual_seed(1024)
+            m = build().to(device).eval()
+            m.rtdf_precision = "bf16"
+            e = m.engine()
+            m.rtdf_frozen = True
+            xs = [synth_on_device(torch, 256, N, 500 + i, device) for i in range(2)]
+            for i in range(4):
+                e.forward(xs[i % 2])
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps2 = 10
+            q0.record()
+            for i in range(steps2):
+                out = e.forward(xs[i % 2])
+            q1.record()
+            torch.cuda.synchronize()
+            ms2 = q0.elapsed_time(q1) / steps2
+            ups = 256 / (ms2 * 1e-3)
+            ceiling = measured_peaks()["bf16_sustained"] * 1e12 / (gflop * 1e9)
+            secondary[name] = {"utt_per_s": ups, "ms_per_step": ms2, "batch": 256, "steps": steps2, "gflop_per_utt": gflop,
+                               "frac_of_bf16_sustained_ceiling": ups / ceiling, "finite": bool(torch.isfinite(out).all())}
+            del m, e, xs, out
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -560,7 +596,7 @@ def run_b200(args):
                          f"{'reference model files (oracle/_ref)' if r['kind'] == 'reference' else 'oracle port'}"}
 
     if rank == 0:
-        T = eng.num_frames(N)
+        T = int(lib.rtdf_num_frames(N))
         line = {
             "metric": METRIC, "value": value, "unit": "utt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -584,6 +620,7 @@ def run_b200(args):
             "parity": parity,
             "sweep": sweep,
             "latency": latency,
+            "secondary": secondary,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "gflop_per_utt": GFLOP_PER_UTT,

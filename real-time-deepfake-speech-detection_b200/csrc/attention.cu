@@ -189,6 +189,7 @@ struct AttWsParams {
   // softmax warpgroup works, K / V arrive as two 256-row boxes (rows past T zero-filled by TMA), S = two N <= 256 MMAs
   // per k-step, O sits at column 448 (S columns consumed before P V is issued; P covers [0, Tk/2 <= 256)).
   int n_buf, buf_cols, o_col, kv_boxes;
+  int reverse;     // items from the last utterance to the first (the rows the QKV projection wrote last are still in L2)
   // RTDF_ATTN_DEBUG bit mask -- timing experiments only, the output is wrong when any bit is set (tools/attention_experiment.py):
   // 1 = no row-max pass, 2 = exp pass on the first chunk only, 4 = no TMA loads, 8 = no S MMAs, 16 = no PV MMAs, 32 = no O store
   int debug;
@@ -245,7 +246,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       for (int i = 0; i < n_local; ++i) {
-        const int item = blockIdx.x + i * gridDim.x;
+        const int item = p.reverse ? p.total_items - 1 - ((int)blockIdx.x + i * (int)gridDim.x) : (int)blockIdx.x + i * (int)gridDim.x;
         const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
         const int s = i % p.n_stages;
         const uint32_t ph = (i / p.n_stages) & 1;
@@ -315,7 +316,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     constexpr int nb = kNb;
     const float kLog2e = 1.4426950408889634f;
     for (int i = g; i < n_local && g < nb; i += nb) {
-      const int item = blockIdx.x + i * gridDim.x;
+      const int item = p.reverse ? p.total_items - 1 - ((int)blockIdx.x + i * (int)gridDim.x) : (int)blockIdx.x + i * (int)gridDim.x;
       const int qt = item % p.n_qt, h = (item / p.n_qt) % p.H, b = item / (p.n_qt * p.H);
       const uint32_t ph = (i / nb) & 1;
       const bool warp_active = qt * 128 + q * 32 < T;        // warp-uniform: any valid query row in this warp
@@ -433,7 +434,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   }
 }
 
-int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H) {
+int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H, bool reverse) {
   RTDF_REQUIRE(qkv && ctx && B > 0 && H > 0, "attention_ws: bad arguments");
   RTDF_REQUIRE(T >= 1 && T <= 512, "attention_ws: T = %d frames unsupported (1..512; <= 10.2 s of audio)", T);
   AttWsParams p;
@@ -447,6 +448,7 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   }
   p.T = T;
   p.H = H;
+  p.reverse = reverse ? 1 : 0;
   p.Tk = (T + 15) & ~15;
   p.n_qt = ceil_div(T, 128);
   const long long items = (long long)B * H * p.n_qt;

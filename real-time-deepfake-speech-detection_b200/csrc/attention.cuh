@@ -11,7 +11,7 @@ namespace rtdf {
 // tcgen05 path (default): persistent warp-specialised kernel -- TMA producer warp, MMA issuer warp, two softmax
 // warpgroups ping-ponging over two TMEM buffers; S = Q K^T (SS), P written back to TMEM, O = P V (TS).  T <= 256 frames
 // use two 256-column buffers; 256 < T <= 512 one 512-column buffer (single softmax warpgroup, K / V in two TMA boxes).
-int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H);
+int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H, bool reverse = false);
 
 // earlier tile kernel, kept for A/B runs: one CTA per (query tile of 128, head, utterance): S = Q K^T in TMEM, fp32 softmax in
 // registers, P (bf16) staged in swizzled smem, O = P V in TMEM.

@@ -499,11 +499,13 @@ ln_rows_generic_kernel(const TIn* __restrict__ in, long long rows, int C, const 
 template <int R, bool kBf16Out>
 __global__ void __launch_bounds__(128)
 ln1024_kernel(const float* __restrict__ in, long long rows, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float eps, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+              float eps, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int reverse) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * R;
+  // reverse: the first CTAs take the LAST rows -- the ones the residual GEMM in front wrote last and L2 still holds
+  const long long blk = reverse ? (long long)gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const long long row0 = (blk * 4 + (threadIdx.x >> 5)) * R;
   if (row0 >= rows) return;
   float4 v[R][8];
 #pragma unroll
@@ -705,18 +707,18 @@ static int ln_variant() {
 
 template <typename TIn>
 static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const float* gamma, const float* beta,
-                     float eps, int act, float* out_f32, bf16* out_bf16) {
+                     float eps, int act, float* out_f32, bf16* out_bf16, bool reverse = false) {
   RTDF_REQUIRE(in && gamma && beta && rows > 0 && C > 0 && (out_f32 || out_bf16), "layernorm_rows: bad arguments");
   if (sizeof(TIn) == 4 && C == 1024 && act == ACT_NONE && (out_f32 != nullptr) != (out_bf16 != nullptr) && ln_variant() > 0) {
     const float* inf = reinterpret_cast<const float*>(in);
     const int R = ln_variant() >= 2 ? 2 : 1;
     const unsigned g = (unsigned)((rows + 4 * R - 1) / (4 * R));
     if (R == 2) {
-      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
-      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
     } else {
-      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
-      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16));
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
     }
     RTDF_LAUNCH_CHECK();
     return RTDF_OK;
@@ -732,8 +734,8 @@ static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const
 }
 
 int layernorm_rows_f32(cudaStream_t s, const float* in, long long rows, int C, const float* gamma, const float* beta,
-                       float eps, int act, float* out_f32, bf16* out_bf16) {
-  return ln_launch<float>(s, in, rows, C, gamma, beta, eps, act, out_f32, out_bf16);
+                       float eps, int act, float* out_f32, bf16* out_bf16, bool reverse) {
+  return ln_launch<float>(s, in, rows, C, gamma, beta, eps, act, out_f32, out_bf16, reverse);
 }
 int layernorm_rows_bf16(cudaStream_t s, const bf16* in, long long rows, int C, const float* gamma, const float* beta,
                         float eps, int act, float* out_f32, bf16* out_bf16) {

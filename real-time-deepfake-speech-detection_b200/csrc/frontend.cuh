@@ -28,8 +28,9 @@ int conv0_gn_gelu(cudaStream_t s, const float* wav, int B, int N, const float* w
                   const float* beta, float eps, float* ws, float* out_f32, bf16* out_bf16);
 
 // Row LayerNorm: in (rows, C) fp32 or bf16 -> optional fp32 and/or bf16 outputs, optional activation.
+// reverse (LayerNorm(1024) fast path only): CTAs walk the rows from the last to the first (see TcEpilogue::reverse_tiles)
 int layernorm_rows_f32(cudaStream_t s, const float* in, long long rows, int C, const float* gamma, const float* beta,
-                       float eps, int act, float* out_f32, bf16* out_bf16);
+                       float eps, int act, float* out_f32, bf16* out_bf16, bool reverse = false);
 int layernorm_rows_bf16(cudaStream_t s, const bf16* in, long long rows, int C, const float* gamma, const float* beta,
                         float eps, int act, float* out_f32, bf16* out_bf16);
 

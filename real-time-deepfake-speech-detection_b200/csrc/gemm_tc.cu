@@ -38,6 +38,8 @@ struct TcKernelParams {
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
   int epi_mode;
   int debug = 0;           // RTDF_GEMM_DEBUG bit mask (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
+  int reverse = 0;         // walk the tiles from the last to the first (TcEpilogue::reverse_tiles): the rows the previous kernel
+                           // wrote last are then read first, while they are still in L2
   int stream_mode = 0;     // streaming-chunk launches under programmatic dependent launch: dependents are released at the
                            // start, and the weight (W) tiles of the first ring round are requested BEFORE waiting for the
                            // previous kernel (they do not depend on it), so the weight stream of kernel k+1 overlaps kernel k
@@ -493,7 +495,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // Weight tiles of the first ring round: requested before the wait on the previous kernel.  The stage barrier
         // expects the bytes of both operands; the A tile follows after the wait.
         for (int t = blockIdx.x; t < p.total_tiles && pre < (uint32_t)kStages; t += gridDim.x) {
-          const int split = t % p.k_splits, tt = t / p.k_splits;
+          const int tile = p.reverse ? p.total_tiles - 1 - t : t;
+        const int split = tile % p.k_splits, tt = tile / p.k_splits;
           const int n0 = (tt % tiles_n) * BN;
           const int kb0 = split * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
           for (int kb = kb0; kb < kb1 && pre < (uint32_t)kStages; ++kb, ++pre) {
@@ -508,7 +511,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       uint32_t it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int split = t % p.k_splits, tt = t / p.k_splits;
+        const int tile = p.reverse ? p.total_tiles - 1 - t : t;
+        const int split = tile % p.k_splits, tt = tile / p.k_splits;
         const int n_tile = tt % tiles_n, m_tile = (tt / tiles_n) % tiles_m, batch = tt / (tiles_n * tiles_m);
         const int m0 = m_tile * BM, n0 = n_tile * BN;
         const int a_col0 = n_tile * p.a_col_per_ntile;
@@ -545,7 +549,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(tempty_bar(a), aph ^ 1);     // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (kLN ? 0 : a * BN);
-        const int kb0 = (t % p.k_splits) * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int kb0 = ((p.reverse ? p.total_tiles - 1 - t : t) % p.k_splits) * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -579,7 +583,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int mode = p.epi_mode;
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++lt) {
-      const int split = t % p.k_splits, tt = t / p.k_splits;
+      const int tile = p.reverse ? p.total_tiles - 1 - t : t;
+        const int split = tile % p.k_splits, tt = tile / p.k_splits;
       const int n_tile = tt % tiles_n, m_tile = (tt / tiles_n) % tiles_m, batch = tt / (tiles_n * tiles_m);
       const int m0 = m_tile * BM, n0 = n_tile * BN;
       const int a = lt % kAcc;
@@ -776,7 +781,8 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       // ===== TMA producer (both CTAs) =====
       uint32_t it = 0;
       for (int t = pair; t < p.total_tiles; t += n_pairs) {
-        const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+        const int tile = p.reverse ? p.total_tiles - 1 - t : t;
+        const int n_tile = tile % tiles_n, m_tile = (tile / tiles_n) % tiles_m, batch = tile / (tiles_n * tiles_m);
         const int m0 = m_tile * 256 + (int)rank * 128, nb0 = n_tile * BN + (int)rank * 128;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % kStages;
@@ -833,7 +839,8 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int mode = p.epi_mode;
     uint32_t lt = 0;
     for (int t = pair; t < p.total_tiles; t += n_pairs, ++lt) {
-      const int n_tile = t % tiles_n, m_tile = (t / tiles_n) % tiles_m, batch = t / (tiles_n * tiles_m);
+      const int tile = p.reverse ? p.total_tiles - 1 - t : t;
+        const int n_tile = tile % tiles_n, m_tile = (tile / tiles_n) % tiles_m, batch = tile / (tiles_n * tiles_m);
       const int m0 = m_tile * 256 + (int)rank * 128, n0 = n_tile * BN;
       const int a = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
@@ -1450,6 +1457,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   }
   p.epi = epi;
+  p.reverse = epi.reverse_tiles ? 1 : 0;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
   p.stream_mode = (pdl_enabled() && !epi.rowln_counters && stream_prefetch_enabled()) ? 1 : 0;
@@ -1527,6 +1535,7 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   p.total_tiles = (int)total;
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
+  p.reverse = epi.reverse_tiles ? 1 : 0;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, false, 256));
   {
@@ -1588,6 +1597,7 @@ static int launch_conv_ln(cudaStream_t stream, const TcOperandA& A, const bf16* 
   p.total_tiles = (int)total;
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
+  p.reverse = epi.reverse_tiles ? 1 : 0;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, true, 512));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_ln_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -1641,6 +1651,7 @@ static int launch_conv_ln_2sm(cudaStream_t stream, const TcOperandA& A, const bf
   p.total_tiles = (int)total;
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
+  p.reverse = epi.reverse_tiles ? 1 : 0;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, true, 512));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_ln_2sm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -22,6 +22,9 @@ struct TcEpilogue {
   const float* ln_gamma = nullptr;
   const float* ln_beta = nullptr;
   float ln_eps = 1e-5f;
+  // Walk the output tiles in reverse order (last row block first).  Consecutive kernels of the transformer stack alternate
+  // direction (model.cu): a kernel then starts on the rows its predecessor wrote last, which are the ones still in L2.
+  bool reverse_tiles = false;
   // ---- LayerNorm folded into the GEMMs on either side of it (bf16 transformer layers, model.cu) -------------------
   // y = LN(x) W^T + b  ==  rstd_i * (bf16(x) W'^T - mean_i * c) + d   with  W' = bf16(W diag(gamma)),  c_j = sum_k W'_jk,
   // d_j = b_j + sum_k beta_k W_jk.  The residual GEMM that produces x also emits what the next GEMM needs:

@@ -695,6 +695,15 @@ static bool conv0_tc_wanted(const rtdf_ctx* c, long long frames) {
   return v == 0 && c->conv0_tc_w && (c->regime == RTDF_REGIME_THROUGHPUT || frames >= 2LL * kNumSMs * 128);
 }
 
+static bool zigzag_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_ZIGZAG");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool conv_2sm_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -880,6 +889,12 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
   // LN(x) W^T + b is evaluated by the projection that follows as rstd_i (bf16(x) W'^T - mean_i c) + d (weights folded at
   // pack time, gemm_tc.cuh TcEpilogue::fold_*), and the bf16 copy of the residual stream plus the per-row (sum, sum of
   // squares) come out of the epilogue of the residual GEMM that produced x.
+  // Zig-zag traversal (bf16, large batches): every kernel of the layer stack walks its row blocks in the opposite direction
+  // of its predecessor, so it starts on the rows that were written last and are still in L2 (each kernel's working set,
+  // 50 - 130 MB, is of the order of the L2 itself).  Tile order does not touch the arithmetic: results are bit-identical.
+  const bool zigzag = bf && zigzag_enabled() && !skinny_rows(c, M);
+  bool rev = false;
+  auto next_dir = [&]() { rev = zigzag ? !rev : false; return rev; };
   const bool fold = bf && c->ln_fold;
   const bool splitk = bf && !layer_taps && skinny_rows(c, M) && w.partials;
   const int sp_out = splitk ? tc_plan_splits(M, 1024, 1024) : 1, sp_fc2 = splitk ? tc_plan_splits(M, 1024, 4096) : 1;
@@ -890,7 +905,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       pending = 0;
       return layernorm_accum_rows(s, w.x, w.partials, np, M, n.g, n.b, 1e-5f, of32, ob16);
     }
-    return layernorm_rows_f32(s, w.x, M, 1024, n.g, n.b, 1e-5f, ACT_NONE, of32, ob16);
+    return layernorm_rows_f32(s, w.x, M, 1024, n.g, n.b, 1e-5f, ACT_NONE, of32, ob16, next_dir());
   };
   auto fold_prep = [&]() -> int {          // folded mode: xb / stats for the next projection, if not produced yet
     if (pending > 1) {
@@ -924,6 +939,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     e.ldr = 1024;
     e.out_f32 = w.x;
     e.ld_f32 = 1024;
+    e.reverse_tiles = next_dir();
     if (fold) {
       e.xb_out = static_cast<bf16*>(w.xb);
       e.stats_out = w.stats;
@@ -942,13 +958,14 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       RTDF_TRY(ln_input(L.ln1, L.qkv, L.qkv_c, L.qkv_d, e));
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.qkv); e.ld_bf16 = 3072; }
       else { e.out_f32 = static_cast<float*>(w.qkv); e.ld_f32 = 3072; }
+      e.reverse_tiles = next_dir();
       RTDF_TRY(linear(c, s, w.xb, M, L.qkv, e));
     }
     if (bf) {
       if (T > 512)   // beyond the tcgen05 kernel's 512 key columns of tensor memory (10.2 s of audio): SIMT kernel
         RTDF_TRY(attention_simt_bf16(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
       else if (c->d.attention_impl == 0)
-        RTDF_TRY(attention_ws(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
+        RTDF_TRY(attention_ws(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16, next_dir()));
       else if (c->d.attention_impl == 2)
         RTDF_TRY(attention_tc(s, static_cast<const bf16*>(w.qkv), static_cast<bf16*>(w.attn), B, T, 16));
       else
@@ -963,6 +980,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       RTDF_TRY(ln_input(L.ln2, L.fc1, L.fc1_c, L.fc1_d, e));
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.hbuf); e.ld_bf16 = 4096; }
       else { e.out_f32 = static_cast<float*>(w.hbuf); e.ld_f32 = 4096; }
+      e.reverse_tiles = next_dir();
       RTDF_TRY(linear(c, s, w.xb, M, L.fc1, e));
     }
     RTDF_TRY(residual_gemm(w.hbuf, L.fc2, sp_fc2));

@@ -116,9 +116,13 @@ class Engine:
 
     def _launch_forward(self, wav, B, N, preemph, coef, logits, ws):
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        native.check(self.lib.rtdf_forward(self._ctx, native.ptr(wav), B, N, int(bool(preemph)), float(coef),
-                                           native.ptr(logits), native.ptr(ws), ws.numel(), None,
-                                           ctypes.c_void_p(stream)), "rtdf_forward")
+        torch.cuda.nvtx.range_push(f"rtdf_forward B={B} N={N} {self.precision}")     # visible in nsys / ncu --nvtx timelines
+        try:
+            native.check(self.lib.rtdf_forward(self._ctx, native.ptr(wav), B, N, int(bool(preemph)), float(coef),
+                                               native.ptr(logits), native.ptr(ws), ws.numel(), None,
+                                               ctypes.c_void_p(stream)), "rtdf_forward")
+        finally:
+            torch.cuda.nvtx.range_pop()
 
     def _graph_entry(self, B, N, preemph, coef, regime, first_input=None):
         """(graph, static_in, static_out) for one input shape; captured on first use."""

@@ -1491,7 +1491,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
     RTDF_CHECK_CUDA(cudaEventCreate(&rec.a));
     RTDF_CHECK_CUDA(cudaEventCreate(&rec.b));
     rec.flops = 2.0 * (double)A.rows_per_batch * (double)A.batches * (double)N * (double)Kw;
-    rec.variant = BN + (BK == 32 ? 1 : 0);
+    rec.variant = epi.profile_as_wide ? 256 : BN + (BK == 32 ? 1 : 0);
     RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
   RTDF_CHECK_CUDA(launch_pdl(tc_gemm_kernel<BN, BK>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, mapA, mapB,

@@ -695,6 +695,17 @@ static bool conv0_tc_wanted(const rtdf_ctx* c, long long frames) {
   return v == 0 && c->conv0_tc_w && (c->regime == RTDF_REGIME_THROUGHPUT || frames >= 2LL * kNumSMs * 128);
 }
 
+static bool tail_split_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // opt-in (r02 experiment, measured SLOWER: 13.03 vs 12.0 ms per step, profiles/r02_tail_split_ab.txt -- the second
+    // persistent kernel's ramp-up / drain costs more than the partial round it removes)
+    const char* e = getenv("RTDF_TAIL_SPLIT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool zigzag_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -725,6 +736,36 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
       // the tile count -- not the tile shape -- sets the time: 64-wide tiles give 4x the CTAs of the 256-wide ones
       // (the residual GEMMs of the transformer layers additionally split K, see run_frontend).
       return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, e);
+    }
+    if (variant == 2256 && !e.xb_out && !e.fold_stats && !e.rowln_counters && tail_split_enabled()) {
+      // Wave quantisation: the persistent CTA-pair kernel walks ceil(tiles / 74) rounds of 256 x 256 tiles, and at the
+      // timed batch the last round is 10 - 70 % empty (out_proj / fc2: 200 tiles = 2.7 rounds).  The row blocks that do
+      // not fill a whole number of rounds go to a second launch with 128 x 128 single-CTA tiles (a quarter of the work
+      // each): its partial last round costs a quarter of a pair-tile time.  Same arithmetic per output element
+      // (K order unchanged), so the result is bit-identical to the one-launch version.
+      const long long tiles_m = (rows + 255) / 256, tiles_n = L.n / 256, pairs = kNumSMs / 2;
+      const long long total = tiles_m * tiles_n;
+      const long long full_rounds = total / pairs;
+      const long long m_split = full_rounds * pairs / tiles_n;            // row blocks of whole rounds
+      if (full_rounds >= 1 && m_split >= 1 && m_split < tiles_m) {
+        const long long tail_rows = rows - m_split * 256;
+        const long long tail_tiles = ((tail_rows + 127) / 128) * ((L.n + 127) / 128);
+        const double before = (double)((total + pairs - 1) / pairs);
+        const double after = (double)((m_split * tiles_n + pairs - 1) / pairs) + 0.29 * (double)((tail_tiles + kNumSMs - 1) / kNumSMs);
+        if (after < 0.97 * before) {
+          const long long r0 = m_split * 256;
+          TcEpilogue et = e;
+          if (et.resid) et.resid += r0 * et.ldr;
+          if (et.out_f32) et.out_f32 += r0 * et.ld_f32;
+          if (et.out_bf16) et.out_bf16 += r0 * et.ld_bf16;
+          et.profile_as_wide = true;
+          const bf16* At = static_cast<const bf16*>(A) + r0 * L.k;
+          if (e.reverse_tiles) RTDF_TRY(tc_gemm(s, plainA(At, tail_rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 128, et));
+          RTDF_TRY(tc_gemm(s, plainA(A, r0, L.k), L.wb, L.n, L.k, TC_PLAIN, 2256, e));
+          if (!e.reverse_tiles) RTDF_TRY(tc_gemm(s, plainA(At, tail_rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 128, et));
+          return RTDF_OK;
+        }
+      }
     }
     return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, variant, e);
   }

@@ -38,6 +38,10 @@ struct TcKernelParams {
   int a_kb_col_step, a_kb_row_step, a_row_off, a_col_per_ntile;
   int epi_mode;
   int debug = 0;           // RTDF_GEMM_DEBUG bit mask (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue
+  // CTA-pair kernel, wave quantisation: work units [0, tail_start) are whole 256-wide tiles; each tile from tail_start on --
+  // the ones that would form a partly empty last round -- is cut into tail_sub column slices (units of 256 / tail_sub
+  // columns, own accumulator, own epilogue), so that the last round costs a fraction of a tile time.  tail_sub = 1: off.
+  int tail_start = 0, tail_sub = 1, total_units = 0;
   int reverse = 0;         // walk the tiles from the last to the first (TcEpilogue::reverse_tiles): the rows the previous kernel
                            // wrote last are then read first, while they are still in L2
   int stream_mode = 0;     // streaming-chunk launches under programmatic dependent launch: dependents are released at the
@@ -77,6 +81,17 @@ int tc_profile_end(int variant, double* ms_total, double* flops_total, int* laun
   if (flops_total) *flops_total = fl;
   if (launches) *launches = n;
   return RTDF_OK;
+}
+
+static bool tail_slices_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // opt-in (r02 experiment, measured SLOWER: out_proj 38 -> 46 us, fc2 90 -> 122 us, profiles/r02_tail_split_ab.txt):
+    // a 64-column slice of a pair tile costs 0.7 of the whole tile -- M = 256 MMAs are bound by the A-operand feed, not N
+    const char* e = getenv("RTDF_TAIL_SLICES");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 static bool stream_prefetch_enabled() {
@@ -249,9 +264,10 @@ template <int BN>
 __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, const CUtensorMap* mapC, int mode, uint32_t t_row,
                                                     const float* sb, int half, int lane, uint8_t* box_gen, uint32_t box,
                                                     int n0, int row0, int batch, long long row, bool row_ok,
-                                                    const LnFold& fold, int n_tile) {
+                                                    const LnFold& fold, int n_tile, int n_limit = 0x7fffffff) {
   constexpr int kColsPerWarp = BN / 2;
   const int c_begin = half * kColsPerWarp, c_end = c_begin + kColsPerWarp;
+  if (n_limit > p.N) n_limit = p.N;       // columns from n_limit on are not part of this work unit
   if (mode == EPI_XRES) {
     // x_new = x_old + v: x_old is read by this thread (its own row), x_new goes back through TMA stores, its bf16 copy and
     // this thread's partial (sum, sum of squares) over its columns go out with plain stores.
@@ -305,7 +321,7 @@ __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, con
   } else if (mode == EPI_TMA_BF16 && kColsPerWarp >= 64) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 64) {
-      if (n0 + c >= p.N) break;  // warp-uniform
+      if (n0 + c >= n_limit) break;  // warp-uniform
       uint32_t r0[32], r1[32];
       tmem_ld32(t_row + c, r0);
       tmem_ld32(t_row + c + 32, r1);
@@ -326,7 +342,7 @@ __device__ __forceinline__ void epilogue_plain_tile(const TcKernelParams& p, con
   } else {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
-      if (n0 + c >= p.N) break;  // warp-uniform
+      if (n0 + c >= n_limit) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld32(t_row + c, r);
       tmem_ld_wait();
@@ -722,10 +738,30 @@ struct Tc2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed + 1024;
 };
 
+struct PairUnit { int n_tile, m_tile, batch, n0, width; };
+__device__ __forceinline__ PairUnit pair_unit(const TcKernelParams& p, int u, int BN) {
+  if (p.reverse) u = p.total_units - 1 - u;
+  int tile = u, sub = 0, width = BN;
+  if (u >= p.tail_start && p.tail_sub > 1) {
+    const int v = u - p.tail_start;
+    tile = p.tail_start + v / p.tail_sub;
+    sub = v % p.tail_sub;
+    width = BN / p.tail_sub;
+  }
+  PairUnit r;
+  r.n_tile = tile % p.tiles_n;
+  r.m_tile = (tile / p.tiles_n) % p.tiles_m;
+  r.batch = tile / (p.tiles_n * p.tiles_m);
+  r.n0 = r.n_tile * BN + sub * width;
+  r.width = width;
+  return r;
+}
+
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BK>::kThreads, 1)
 tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   const __grid_constant__ CUtensorMap mapC, const TcKernelParams p) {
+                   const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapBn,
+                   const TcKernelParams p) {
   using Cfg = Tc2Cfg<BK>;
   constexpr int BN = Cfg::BN;
   constexpr int kStages = Cfg::kStages;
@@ -780,10 +816,12 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (lane == 0) {
       // ===== TMA producer (both CTAs) =====
       uint32_t it = 0;
-      for (int t = pair; t < p.total_tiles; t += n_pairs) {
-        const int tile = p.reverse ? p.total_tiles - 1 - t : t;
-        const int n_tile = tile % tiles_n, m_tile = (tile / tiles_n) % tiles_m, batch = tile / (tiles_n * tiles_m);
-        const int m0 = m_tile * 256 + (int)rank * 128, nb0 = n_tile * BN + (int)rank * 128;
+      for (int t = pair; t < p.total_units; t += n_pairs) {
+        const PairUnit u = pair_unit(p, t, BN);
+        const int m0 = u.m_tile * 256 + (int)rank * 128, batch = u.batch;
+        const bool narrow = u.width != BN;                   // column slice of a tail tile: this CTA's half = width / 2 W rows
+        const int nb0 = u.n0 + (int)rank * (u.width >> 1);
+        const uint32_t unit_bytes = 2u * (Cfg::kABytes + (uint32_t)(u.width >> 1) * BK * 2);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -792,20 +830,22 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             if (leader) mbar_arrive(full_bar(s));
             continue;
           }
-          if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+          if (leader) mbar_expect_tx(full_bar(s), unit_bytes);
           const uint32_t full_leader = mapa_shared(full_bar(s), 0);
           const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
           tma_load_3d_2sm(a_dst, &mapA, full_leader, kb * BK, m0, batch);
-          tma_load_2d_2sm(a_dst + Cfg::kABytes, &mapB, full_leader, kb * BK, nb0);
+          tma_load_2d_2sm(a_dst + Cfg::kABytes, narrow ? &mapBn : &mapB, full_leader, kb * BK, nb0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ===== MMA issuer (leader CTA only) =====
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      constexpr uint32_t idesc_full = umma_idesc_bf16(256, BN);
+      const uint32_t idesc_narrow = umma_idesc_bf16(256, BN / (p.tail_sub > 1 ? p.tail_sub : 1));
       uint32_t it = 0, lt = 0;
-      for (int t = pair; t < p.total_tiles; t += n_pairs, ++lt) {
+      for (int t = pair; t < p.total_units; t += n_pairs, ++lt) {
+        const uint32_t idesc = pair_unit(p, t, BN).width != BN ? idesc_narrow : idesc_full;
         const int a = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(tempty_bar(a), aph ^ 1);
@@ -838,10 +878,10 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t box = smem_base + kOffStaging + (warp - 2) * 4096;
     const int mode = p.epi_mode;
     uint32_t lt = 0;
-    for (int t = pair; t < p.total_tiles; t += n_pairs, ++lt) {
-      const int tile = p.reverse ? p.total_tiles - 1 - t : t;
-        const int n_tile = tile % tiles_n, m_tile = (tile / tiles_n) % tiles_m, batch = tile / (tiles_n * tiles_m);
-      const int m0 = m_tile * 256 + (int)rank * 128, n0 = n_tile * BN;
+    for (int t = pair; t < p.total_units; t += n_pairs, ++lt) {
+      const PairUnit u = pair_unit(p, t, BN);
+      const int n_tile = u.n_tile, m_tile = u.m_tile, batch = u.batch;
+      const int m0 = m_tile * 256 + (int)rank * 128, n0 = u.n0;
       const int a = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       const int row0 = m0 + q * 32;
@@ -856,8 +896,13 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       __syncwarp();
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-      if (!(p.debug & 4))
-        epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok, fold, n_tile);
+      if (!(p.debug & 4)) {
+        if (u.width == BN)
+          epilogue_plain_tile<BN>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok, fold, n_tile);
+        else   // column slice of a tail tile (<= 64 columns): the warps of column half 0 take it, 64 columns each
+          epilogue_plain_tile<128>(p, &mapC, mode, t_row, sb, half, lane, box_gen, box, n0, row0, batch, row, row_ok, fold, n_tile,
+                                   n0 + u.width);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(a), 0));
@@ -1511,7 +1556,7 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   using Cfg = Tc2Cfg<BK>;
   static_assert(Cfg::kStages >= 3, "need at least three stages");
   static_assert(8 * (2 * Cfg::kStages + 5) <= 256, "barrier block too small");
-  CUtensorMap mapA, mapB, mapC;
+  CUtensorMap mapA, mapB, mapBn, mapC;
   {
     uint64_t dims[3] = {(uint64_t)A.k_extent, (uint64_t)A.rows_per_batch, (uint64_t)A.batches};
     uint64_t strides[2] = {(uint64_t)A.row_stride * 2, (uint64_t)(A.batches > 1 ? A.batch_stride : A.row_stride * A.rows_per_batch) * 2};
@@ -1523,6 +1568,8 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
     uint64_t strides[1] = {(uint64_t)Kw * 2};
     uint32_t box[2] = {(uint32_t)BK, 128};
     RTDF_TRY(make_tmap_bf16(&mapB, W, 2, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
+    box[1] = 32;       // this CTA's half of a 64-column slice of a tail tile
+    RTDF_TRY(make_tmap_bf16(&mapBn, W, 2, dims, strides, box, BK == 64 ? TMAP_SW128 : TMAP_SW64));
   }
   TcKernelParams p;
   p.rows_per_batch = (int)A.rows_per_batch;
@@ -1531,13 +1578,33 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   p.tiles_n = ceil_div(N, 256);
   p.tiles_m = ceil_div((int)A.rows_per_batch, 256);
   const long long total = (long long)p.tiles_n * p.tiles_m * A.batches;
-  RTDF_REQUIRE(total < (1LL << 31), "tc_gemm: too many tiles");
+  RTDF_REQUIRE(total < (1LL << 29), "tc_gemm: too many tiles");
   p.total_tiles = (int)total;
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
   p.reverse = epi.reverse_tiles ? 1 : 0;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, false, 256));
+  // Wave quantisation: with more tiles than CTA pairs the last round of the persistent loop is partly empty (out_proj /
+  // fc2 at the timed batch: 200 tiles on 74 pairs = 2.7 rounds).  The tiles of that round are cut into four 64-column
+  // slices each -- same kernel, narrower MMAs -- when the model says the round gets cheaper: a slice costs about 0.32 of
+  // a tile (a quarter of the math, the A tile loaded again).
+  const int n_pairs_h = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
+  p.tail_start = p.total_tiles;
+  p.tail_sub = 1;
+  p.total_units = p.total_tiles;
+  {
+    const int full_rounds = p.total_tiles / n_pairs_h, rem = p.total_tiles % n_pairs_h;
+    const bool plain_epi = !epi.xb_out && !epi.rowln_counters && !epi.partials && N % 256 == 0;
+    if (tail_slices_enabled() && plain_epi && full_rounds >= 1 && rem > 0) {
+      const int slice_rounds = ceil_div(rem * 4, n_pairs_h);
+      if (0.32 * slice_rounds < 1.0) {
+        p.tail_start = full_rounds * n_pairs_h;
+        p.tail_sub = 4;
+        p.total_units = p.tail_start + rem * 4;
+      }
+    }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -1557,7 +1624,7 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
     RTDF_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
   RTDF_CHECK_CUDA(launch_pdl(tc_gemm_2sm_kernel<BK>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, mapA, mapB,
-                             mapC, p));
+                             mapC, mapBn, p));
   RTDF_LAUNCH_CHECK();
   if (g_prof_on) {
     RTDF_CHECK_CUDA(cudaEventRecord(rec.b, stream));

@@ -199,3 +199,25 @@ def test_streaming_static_buffers_match_forward():
         got = eng.forward_static(1, 16000).cpu()
         assert torch.equal(got, want[i]), i
     assert torch.equal(eng.forward(buf).cpu(), want[2])       # the static buffer itself is accepted without a copy
+
+
+def test_engine_cache_invalidation_and_regime_argument():
+    """engine_for re-packs when a parameter's version counter moves; a write through .data is invisible to it until
+    rtdf_runtime.invalidate(model); unknown regimes are rejected."""
+    _, prod = build_pair("My_XLSR_AASIST", "bf16", num_layers=1, order="first")
+    rt = pkg("rtdf_runtime")
+    from oracle import models_ref as O
+    x = O.synth_waveforms(2, 16000, seed=21).cuda()
+    y0 = prod(x).clone()
+    eng0 = prod.engine()
+    with torch.no_grad():
+        prod.out_layer.bias.add_(0.5)                      # in-place op: version counter moves, engine rebuilt
+    assert prod.engine() is not eng0
+    y1 = prod(x)
+    assert float((y1 - y0 - 0.5).abs().max()) < 1e-5
+    prod.out_layer.bias.data.add_(0.25)                    # .data write: not seen ...
+    assert float((prod(x) - y1).abs().max()) == 0.0
+    rt.invalidate(prod)                                    # ... until the cached engine is dropped
+    assert float((prod(x) - y1 - 0.25).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        prod.engine().forward(x, regime="fastest")

@@ -26,6 +26,7 @@ constexpr int kEpiThreads = 256;
 struct KParams {
   long long rows;
   int Hp, Wp, n_chunks, n_sub, shift_min, slab_rows, n_stages, total_tiles;
+  int n_boxes, box_rows;         // a slab of more than 256 rows (planes wider than 124 columns) arrives as two TMA boxes
   int a_off[kConvTcMaxChunks];   // byte offset of chunk c's first A row inside the hi (or lo) region of a stage
   int hp_lo, hp_hi;
   const float *bias, *s1, *t1, *resid, *s2, *t2;
@@ -135,10 +136,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         mbar_expect_tx(full_bar(s), stage_bytes);
         const uint32_t dst = smem_base + off_stages + s * stage_bytes;
         const int row0 = t * kTileM + p.shift_min;        // may be negative / run past the end: TMA zero-fills
-        for (int b = 0; b < p.n_sub; ++b) {
-          tma_load_2d(dst + b * slab_bytes, &mapAhi, full_bar(s), b * 64, row0);
-          if (NS > 1) tma_load_2d(dst + a_half_bytes + b * slab_bytes, &mapAlo, full_bar(s), b * 64, row0);
-        }
+        for (int b = 0; b < p.n_sub; ++b)
+          for (int bx = 0; bx < p.n_boxes; ++bx) {
+            const int off = bx * p.box_rows * kRowBytes;
+            tma_load_2d(dst + b * slab_bytes + off, &mapAhi, full_bar(s), b * 64, row0 + bx * p.box_rows);
+            if (NS > 1) tma_load_2d(dst + a_half_bytes + b * slab_bytes + off, &mapAlo, full_bar(s), b * 64, row0 + bx * p.box_rows);
+          }
       }
     }
   } else if (warp == 1) {
@@ -288,7 +291,14 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
   }
   p.shift_min = smin;
   p.slab_rows = ((kTileM + (smax - smin) + 15) / 16) * 16;
-  RTDF_REQUIRE(p.slab_rows <= 256, "conv_tc: tap span %d rows too wide for one TMA box (plane width %d)", smax - smin, a.Wp);
+  p.n_boxes = 1;
+  p.box_rows = p.slab_rows;
+  if (p.slab_rows > 256) {       // two boxes of half the slab each (a multiple of 8 rows: whole swizzle atoms)
+    p.n_boxes = 2;
+    p.box_rows = ((p.slab_rows + 1) / 2 + 7) / 8 * 8;
+    p.slab_rows = 2 * p.box_rows;
+  }
+  RTDF_REQUIRE(p.box_rows <= 256, "conv_tc: tap span %d rows too wide for two TMA boxes (plane width %d)", smax - smin, a.Wp);
   const int slab_bytes = p.slab_rows * KW * 2;
   for (int c = 0; c < a.n_chunks; ++c) {
     RTDF_REQUIRE(a.sub[c] >= 0 && a.sub[c] < p.n_sub, "conv_tc: chunk %d reads channel block %d of %d", c, a.sub[c], p.n_sub);
@@ -324,7 +334,7 @@ int launch(cudaStream_t stream, const ConvTcArgs& a) {
   {
     uint64_t dims[2] = {(uint64_t)a.ci, (uint64_t)a.rows};
     uint64_t strides[1] = {(uint64_t)a.ci * 2};
-    uint32_t box[2] = {(uint32_t)KW, (uint32_t)p.slab_rows};
+    uint32_t box[2] = {(uint32_t)KW, (uint32_t)p.box_rows};
     RTDF_TRY(make_tmap_bf16(&mAh, a.in_hi, 2, dims, strides, box, sw));
     if (NS > 1) RTDF_TRY(make_tmap_bf16(&mAl, a.in_lo, 2, dims, strides, box, sw));
     else mAl = mAh;

@@ -1163,8 +1163,11 @@ static int run_aasist(rtdf_ctx* c, cudaStream_t s, const float* feats, int B, in
   const bool bf = c->d.precision == RTDF_PREC_BF16;
   const long long M = (long long)B * T;
   const int Tp = T / 3, kT = Tp / 2 > 0 ? Tp / 2 : 1, kT2 = kT / 2 > 0 ? kT / 2 : 1;
-  // T' = T/3 temporal nodes: the shifted-row convs read a slab of 128 + T' + 4 plane rows through one TMA box (<= 256 rows)
-  RTDF_REQUIRE(Tp >= 1 && Tp <= 124, "AASIST back-end supports 3..374 frames (up to 7.4 s of audio), got T = %d", T);
+  // T' = T/3 temporal nodes (graph kernels: up to 256 nodes; shifted-row convs: slab of 128 + T' + 4 plane rows through one
+  // or two TMA boxes).  bf16: up to 512 frames (10.2 s), the reach of the tcgen05 attention; fp32 verification mode: 386.
+  const int max_tp = aasist_tc(c) ? 170 : 128;
+  RTDF_REQUIRE(Tp >= 1 && Tp <= max_tp, "AASIST back-end supports 3..%d frames (%.1f s of audio) in this mode, got T = %d",
+               max_tp * 3 + 2, (max_tp * 3 + 2) * 0.02, T);
   {
     TcEpilogue e;
     e.bias = a.LL.b;

@@ -415,6 +415,8 @@ CONV_PLANES_CASES = [  # (kind, ci, co, B, W)
     ("conv1", 32, 32, 2, 16), ("conv1", 32, 64, 1, 66), ("conv1", 64, 64, 2, 66), ("conv2", 32, 32, 2, 66),
     ("conv2", 64, 64, 3, 67), ("ds", 32, 64, 2, 66), ("lin", 64, 128, 2, 66), ("lin", 128, 64, 2, 16),
     ("conv2", 64, 64, 1, 96),
+    # planes wider than 124 columns: the 128 + W + 4 row slab arrives as two TMA boxes (utterances of 7.5 .. 10.2 s)
+    ("conv1", 64, 64, 1, 170), ("conv2", 32, 32, 2, 150), ("ds", 32, 64, 1, 170), ("conv2", 64, 64, 1, 133),
 ]
 # the timed configuration: B = 64, T' = 66 -> 64 * 44 * 68 = 191,488 plane rows = 1,496 row tiles on 148 persistent CTAs
 CONV_PLANES_CASES_TIMED = [("conv1", 64, 64, 64, 66), ("conv1", 32, 64, 64, 66), ("conv2", 64, 64, 64, 66),

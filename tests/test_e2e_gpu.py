@@ -77,10 +77,13 @@ def test_ragged_batches_preemphasis_determinism():
 
 def test_utterances_longer_than_one_attention_tile():
     """256 < T <= 512 frames (5.1 .. 10.2 s): the transformer's attention stays on tcgen05 (single 512-column TMEM buffer);
-    the AASIST back-end reaches 374 frames (7.4 s), the Conformer ~400 (beyond that the call raises, see test_errors_are_loud)."""
+    the AASIST back-end reaches 512 frames (10.2 s; 386 in fp32 mode), the Conformer ~400 (beyond that the call raises, see
+    test_errors_are_loud)."""
     ec.check_e2e("My_XLSR_AASIST", "bf16", B=1, N=88000, num_layers=2, order="first")       # 5.5 s, T = 274
     ec.check_e2e("My_XLSR_AASIST", "bf16", B=2, N=119000, num_layers=2, order="first")      # 7.4 s, T = 371, T' = 123 nodes
     ec.check_e2e("My_XLSR_AASIST", "fp32", B=1, N=119000, num_layers=1, order="first")
+    ec.check_e2e("My_XLSR_AASIST", "bf16", B=2, N=164000, num_layers=2, order="first")      # 10.2 s, T = 512, T' = 170 nodes:
+    # the transformer's single-buffer attention and the two-box conv slabs of the AASIST encoder at their limit
     ec.check_e2e("MyModel", "bf16", B=1, N=100000, num_layers=2, fixed_call=True)            # 6.25 s, T = 312
 
 
@@ -96,4 +99,4 @@ def test_errors_are_loud():
     with pytest.raises((RuntimeError, ValueError)):
         prod(torch.zeros(1, 100, device="cuda"))          # shorter than the conv receptive field
     with pytest.raises(RuntimeError):
-        prod(torch.zeros(1, 16000 * 8, device="cuda"))    # T = 399 frames: beyond the AASIST back-end's 374
+        prod(torch.zeros(1, 16000 * 11, device="cuda"))   # T = 549 frames: beyond the tcgen05 attention / AASIST reach of 512

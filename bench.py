@@ -503,7 +503,7 @@ def run_b200(args):
         barrier()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
-        gathered = scoring.score_utterances(model, n_items, load_batch, N, B, device, rank=rank, world=world)
+        gathered = scoring.score_utterances(model, n_items, load_batch, N, B, device, rank=rank, world=world, zero_copy=True)
         w1.record()
         barrier()
         ms_sweep = max_over_ranks(w0.elapsed_time(w1))

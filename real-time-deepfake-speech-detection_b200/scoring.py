@@ -121,25 +121,36 @@ class ScoringPipeline:
 
 
 def score_utterances(model, n_items, load_batch, n_samples, batch_size, device, rank=0, world=1, group=None,
-                     preemph=False, coef=0.97):
+                     preemph=False, coef=0.97, zero_copy=False):
     """Score items [0, n_items) sharded over `world` ranks; returns all scores (fp32, global order) on every rank.
 
     load_batch(lo, hi, out): fills the pinned host tensor `out` (hi-lo, n_samples) with utterances lo..hi-1
     (the reference's DataLoader role, main.py:200-209) and returns None -- or returns its own (hi-lo, n_samples) fp32
     CPU tensor (ideally pinned, e.g. a slice of a resident pool), which is then copied to the device instead of `out`
-    and must stay untouched until this call returns.  `model` is one of this package's model classes in eval mode on
+    and must stay untouched until this call returns (zero_copy=True: load_batch is called with out=None and MUST return
+    the batch -- no pinned staging buffers are allocated at all).  `model` is one of this package's model classes in eval mode on
     `device`.  The forwards run in the throughput regime, so a score does not depend on the batch or shard an utterance
     lands in: the returned vector is bit-identical for every `world` / `batch_size`.
     """
     lo, hi, per = shard_range(n_items, rank, world)
     pipe = ScoringPipeline(model, max(hi - lo, 1), batch_size, n_samples, device, preemph=preemph, coef=coef, depth=2)
-    host = [torch.empty(batch_size, n_samples, dtype=torch.float32).pin_memory() for _ in range(3)]
+    host = [None, None, None]     # pinned staging buffers, allocated on first use (a zero-copy load_batch never needs them)
+
     for i, (b_lo, b_hi) in enumerate(batch_ranges(lo, hi, batch_size)):
         # 3 host buffers for 2 device slots: push(i) waits for forward(i-2), whose H2D (the last reader of buffer
         # (i-2) % 3 ... and of buffer i % 3 = (i-3) % 3) is then complete
-        out = host[i % 3][: b_hi - b_lo]
-        own = load_batch(b_lo, b_hi, out)
-        pipe.push(out if own is None else own)
+        if zero_copy:
+            own = load_batch(b_lo, b_hi, None)
+            if own is None:
+                raise ValueError("score_utterances(zero_copy=True): load_batch must return the batch tensor")
+        else:
+            if host[i % 3] is None:
+                host[i % 3] = torch.empty(batch_size, n_samples, dtype=torch.float32).pin_memory()
+            out = host[i % 3][: b_hi - b_lo]
+            own = load_batch(b_lo, b_hi, out)
+            if own is None:
+                own = out
+        pipe.push(own)
     torch.cuda.current_stream(torch.device(device)).synchronize()
     return gather_scores(pipe.device_scores(), n_items, per, group)
 

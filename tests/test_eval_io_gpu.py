@@ -181,7 +181,7 @@ def test_scoring_pipeline_matches_direct_forward_bit_exactly():
     all_scores = scoring.score_utterances(prod, 11, load, N, B, "cuda")
     assert torch.equal(all_scores.cpu(), want)
     pool = x.pin_memory()
-    zero_copy = scoring.score_utterances(prod, 11, lambda lo, hi, out: pool[lo:hi], N, 3, "cuda")   # other batch size
+    zero_copy = scoring.score_utterances(prod, 11, lambda lo, hi, out: pool[lo:hi], N, 3, "cuda", zero_copy=True)   # other batch size
     assert torch.equal(zero_copy.cpu(), want)
 
 

@@ -503,6 +503,8 @@ ln1024_kernel(const float* __restrict__ in, long long rows, const float* __restr
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
+  const bool plain_loads = (reverse & 2) != 0;     // bit 1: read x with default caching instead of evict-first (ld.global.cs)
+  reverse &= 1;
   // reverse: the first CTAs take the LAST rows -- the ones the residual GEMM in front wrote last and L2 still holds
   const long long blk = reverse ? (long long)gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const long long row0 = (blk * 4 + (threadIdx.x >> 5)) * R;
@@ -512,8 +514,9 @@ ln1024_kernel(const float* __restrict__ in, long long rows, const float* __restr
   for (int u = 0; u < R; ++u)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[u][j] = row0 + u < rows ? __ldcs(reinterpret_cast<const float4*>(in + (row0 + u) * 1024 + j * 128 + lane * 4))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[u][j] = row0 + u >= rows ? make_float4(0.f, 0.f, 0.f, 0.f)
+                : plain_loads ? *reinterpret_cast<const float4*>(in + (row0 + u) * 1024 + j * 128 + lane * 4)
+                              : __ldcs(reinterpret_cast<const float4*>(in + (row0 + u) * 1024 + j * 128 + lane * 4));
   float mean[R], rstd[R];
 #pragma unroll
   for (int u = 0; u < R; ++u) {
@@ -696,6 +699,15 @@ int layernorm_accum_rows(cudaStream_t s, float* x, const float* partials, int n_
   return RTDF_OK;
 }
 
+static int ln_plain_loads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_LN_LOAD");
+    v = (e && e[0] == '1') ? 2 : 0;
+  }
+  return v;
+}
+
 static int ln_variant() {
   static int v = -1;
   if (v < 0) {
@@ -714,11 +726,11 @@ static int ln_launch(cudaStream_t s, const TIn* in, long long rows, int C, const
     const int R = ln_variant() >= 2 ? 2 : 1;
     const unsigned g = (unsigned)((rows + 4 * R - 1) / (4 * R));
     if (R == 2) {
-      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
-      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, (reverse ? 1 : 0) | ln_plain_loads()));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<2, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, (reverse ? 1 : 0) | ln_plain_loads()));
     } else {
-      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
-      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, reverse ? 1 : 0));
+      if (out_bf16) RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, true>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, (reverse ? 1 : 0) | ln_plain_loads()));
+      else RTDF_CHECK_CUDA(launch_pdl(ln1024_kernel<1, false>, dim3(g), dim3(128), 0, s, inf, rows, gamma, beta, eps, out_f32, out_bf16, (reverse ? 1 : 0) | ln_plain_loads()));
     }
     RTDF_LAUNCH_CHECK();
     return RTDF_OK;

@@ -42,6 +42,8 @@ struct TcKernelParams {
   // the ones that would form a partly empty last round -- is cut into tail_sub column slices (units of 256 / tail_sub
   // columns, own accumulator, own epilogue), so that the last round costs a fraction of a tile time.  tail_sub = 1: off.
   int tail_start = 0, tail_sub = 1, total_units = 0;
+  int a_hint = 0;          // L2 policy of the A-operand loads: 0 default, 1 evict_first (the activation is dead after this GEMM:
+                           // do not let it push the residual stream / the outputs out of L2), 2 evict_last
   int reverse = 0;         // walk the tiles from the last to the first (TcEpilogue::reverse_tiles): the rows the previous kernel
                            // wrote last are then read first, while they are still in L2
   int stream_mode = 0;     // streaming-chunk launches under programmatic dependent launch: dependents are released at the
@@ -542,8 +544,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(empty_bar(s), ph ^ 1);
             mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           }
-          tma_load_3d(a_dst, &mapA, full_bar(s), a_col0 + kb * p.a_kb_col_step,
-                      m0 + p.a_row_off + kb * p.a_kb_row_step, batch);
+          if (p.a_hint)
+            tma_load_3d_hint(a_dst, &mapA, full_bar(s), a_col0 + kb * p.a_kb_col_step,
+                             m0 + p.a_row_off + kb * p.a_kb_row_step, batch,
+                             p.a_hint == 2 ? l2_policy_evict_last() : l2_policy_evict_first());
+          else
+            tma_load_3d(a_dst, &mapA, full_bar(s), a_col0 + kb * p.a_kb_col_step,
+                        m0 + p.a_row_off + kb * p.a_kb_row_step, batch);
           if (it >= pre) {
 #pragma unroll
             for (int h = 0; h < (BN + 255) / 256; ++h)
@@ -815,6 +822,7 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer (both CTAs) =====
+      const uint64_t a_policy = p.a_hint == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
       uint32_t it = 0;
       for (int t = pair; t < p.total_units; t += n_pairs) {
         const PairUnit u = pair_unit(p, t, BN);
@@ -833,7 +841,8 @@ tc_gemm_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (leader) mbar_expect_tx(full_bar(s), unit_bytes);
           const uint32_t full_leader = mapa_shared(full_bar(s), 0);
           const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
-          tma_load_3d_2sm(a_dst, &mapA, full_leader, kb * BK, m0, batch);
+          if (p.a_hint) tma_load_3d_2sm_hint(a_dst, &mapA, full_leader, kb * BK, m0, batch, a_policy);
+          else tma_load_3d_2sm(a_dst, &mapA, full_leader, kb * BK, m0, batch);
           tma_load_2d_2sm(a_dst + Cfg::kABytes, narrow ? &mapBn : &mapB, full_leader, kb * BK, nb0);
         }
       }
@@ -1503,6 +1512,7 @@ static int launch_variant(cudaStream_t stream, const TcOperandA& A, const bf16* 
   }
   p.epi = epi;
   p.reverse = epi.reverse_tiles ? 1 : 0;
+  p.a_hint = epi.a_cache_hint;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, Cfg::kLN, BN));
   p.stream_mode = (pdl_enabled() && !epi.rowln_counters && stream_prefetch_enabled()) ? 1 : 0;
@@ -1583,6 +1593,7 @@ static int launch_2sm(cudaStream_t stream, const TcOperandA& A, const bf16* W, i
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
   p.reverse = epi.reverse_tiles ? 1 : 0;
+  p.a_hint = epi.a_cache_hint;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, false, 256));
   // Wave quantisation: with more tiles than CTA pairs the last round of the persistent loop is partly empty (out_proj /
@@ -1665,6 +1676,7 @@ static int launch_conv_ln(cudaStream_t stream, const TcOperandA& A, const bf16* 
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
   p.reverse = epi.reverse_tiles ? 1 : 0;
+  p.a_hint = epi.a_cache_hint;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, true, 512));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_ln_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -1719,6 +1731,7 @@ static int launch_conv_ln_2sm(cudaStream_t stream, const TcOperandA& A, const bf
   p.a_kb_col_step = BK; p.a_kb_row_step = 0; p.a_row_off = 0; p.a_col_per_ntile = 0;
   p.epi = epi;
   p.reverse = epi.reverse_tiles ? 1 : 0;
+  p.a_hint = epi.a_cache_hint;
   if (p.epi.act == ACT_GELU && g_gelu_override) p.epi.act = g_gelu_override;
   RTDF_TRY(choose_epilogue_mode(p, &mapC, &mapA, A, N, epi, true, 512));
   RTDF_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_ln_2sm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

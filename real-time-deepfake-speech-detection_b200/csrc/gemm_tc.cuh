@@ -25,6 +25,7 @@ struct TcEpilogue {
   // Walk the output tiles in reverse order (last row block first).  Consecutive kernels of the transformer stack alternate
   // direction (model.cu): a kernel then starts on the rows its predecessor wrote last, which are the ones still in L2.
   bool reverse_tiles = false;
+  int a_cache_hint = 0;            // L2 policy of the A-operand loads: 0 default, 1 evict_first, 2 evict_last
   bool profile_as_wide = false;    // per-launch timing: book this launch with the 256-wide tiles (the 128-wide tail of a split GEMM)
   // ---- LayerNorm folded into the GEMMs on either side of it (bf16 transformer layers, model.cu) -------------------
   // y = LN(x) W^T + b  ==  rstd_i * (bf16(x) W'^T - mean_i * c) + d   with  W' = bf16(W diag(gamma)),  c_j = sum_k W'_jk,

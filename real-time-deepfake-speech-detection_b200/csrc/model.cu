@@ -706,6 +706,16 @@ static bool tail_split_enabled() {
   return v == 1;
 }
 
+// L2 policy for the A operand of the transformer projections (activations that are dead once the GEMM has read them)
+static int a_hint_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTDF_A_HINT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static bool zigzag_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -981,6 +991,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     e.out_f32 = w.x;
     e.ld_f32 = 1024;
     e.reverse_tiles = next_dir();
+    e.a_cache_hint = bf ? a_hint_mode() : 0;
     if (fold) {
       e.xb_out = static_cast<bf16*>(w.xb);
       e.stats_out = w.stats;
@@ -1000,6 +1011,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.qkv); e.ld_bf16 = 3072; }
       else { e.out_f32 = static_cast<float*>(w.qkv); e.ld_f32 = 3072; }
       e.reverse_tiles = next_dir();
+      e.a_cache_hint = bf ? a_hint_mode() : 0;
       RTDF_TRY(linear(c, s, w.xb, M, L.qkv, e));
     }
     if (bf) {
@@ -1022,6 +1034,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
       if (bf) { e.out_bf16 = static_cast<bf16*>(w.hbuf); e.ld_bf16 = 4096; }
       else { e.out_f32 = static_cast<float*>(w.hbuf); e.ld_f32 = 4096; }
       e.reverse_tiles = next_dir();
+      e.a_cache_hint = bf ? a_hint_mode() : 0;
       RTDF_TRY(linear(c, s, w.xb, M, L.fc1, e));
     }
     RTDF_TRY(residual_gemm(w.hbuf, L.fc2, sp_fc2));

@@ -50,6 +50,7 @@ def main():
 
     import torch
     import main as ref_main                        # the reference's main.py
+    import main_kd as ref_main_kd                  # the reference's main_kd.py (student / teacher scoring entry point)
     import trainer as ref_trainer                  # the reference's trainer.py
     import models
     import utils
@@ -64,6 +65,8 @@ def main():
     model_class = vars(ref_main)["My_XLSR_AASIST"]
     assert model_class.__module__ == "models.xlsr_aasist", model_class.__module__
     assert vars(ref_main)["ConformerModel"].__module__ == "models.conformer_baseline"
+    assert vars(ref_main_kd)["MyConformerModel"].__module__ == "models.conformer_baseline"      # main_kd.py:20-22
+    assert vars(ref_main_kd)["My_XLSR_AASIST"].__module__ == "models.xlsr_aasist"
     assert utils.f_state_dict_wrapper({"module.a": 1})  # the reference's own helper is the one in use
 
     n_utt, n_samples, batch = 8, 16000, 3          # ragged last batch of 2 (drop_last=False); a last batch of 1 would hit

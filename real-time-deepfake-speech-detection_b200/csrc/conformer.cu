@@ -32,27 +32,32 @@ template <typename T_>
 __global__ void __launch_bounds__(256)
 conformer_attn_kernel(const T_* __restrict__ qkv, const float* __restrict__ rel, T_* __restrict__ out, int n,
                       int heads, int dh, float scale) {
-  extern __shared__ float sm[];
-  const int P = dh + 1;
+  // K, V and the relative-position rows are kept in the I/O type (bf16 in bf16 mode: exact for K / V, the table is rounded
+  // like in the tensor-core kernel), so that utterances of up to 512 frames fit; only the n + 31 table rows this CTA's 32
+  // queries can reach are loaded: row (i - j) + n - 1 for i in [i0, i0 + 32), j in [0, n)  ->  [i0, i0 + n + 30].
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int P = dh + (sizeof(T_) == 2 ? 2 : 1);
   const int np = (n + 31) & ~31;
-  float* sK = sm;                        // [n][P]
-  float* sV = sK + (size_t)n * P;        // [n][dh]
-  float* sE = sV + (size_t)n * dh;       // [2n-1][P]
-  float* sQ = sE + (size_t)(2 * n - 1) * P;  // [8][64]
-  float* sP = sQ + 8 * 64;               // [8][np]
+  const int i0 = blockIdx.y * 32;
+  const int ne = n + 31;
+  T_* sK = reinterpret_cast<T_*>(sm_raw);  // [n][P]
+  T_* sV = sK + (size_t)n * P;             // [n][dh]
+  T_* sE = sV + (size_t)n * dh;            // [n + 31][P]   (table row i0 + r)
+  float* sQ = reinterpret_cast<float*>(sm_raw + ((((size_t)n * P + (size_t)n * dh + (size_t)ne * P) * sizeof(T_) + 15) & ~(size_t)15));  // [8][64]
+  float* sP = sQ + 8 * 64;                 // [8][np]
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int E = heads * dh, ld = 3 * E;
   const T_* base = qkv + (long long)b * n * ld;
   for (int i = threadIdx.x; i < n * dh; i += 256) {
     const int t = i / dh, d = i % dh;
-    sK[t * P + d] = to_f32(base[(long long)t * ld + E + h * dh + d]);
-    sV[t * dh + d] = to_f32(base[(long long)t * ld + 2 * E + h * dh + d]);
+    sK[t * P + d] = base[(long long)t * ld + E + h * dh + d];
+    sV[t * dh + d] = base[(long long)t * ld + 2 * E + h * dh + d];
   }
-  for (int i = threadIdx.x; i < (2 * n - 1) * dh; i += 256) {
+  for (int i = threadIdx.x; i < ne * dh; i += 256) {
     const int r = i / dh, d = i % dh;
-    int relpos = r - (n - 1);
+    int relpos = i0 + r - (n - 1);
     relpos = max(-512, min(512, relpos)) + 512;
-    sE[r * P + d] = rel[relpos * dh + d];
+    sE[r * P + d] = from_f32<T_>(rel[relpos * dh + d]);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,12 +72,12 @@ conformer_attn_kernel(const T_* __restrict__ qkv, const float* __restrict__ rel,
     for (int j = lane; j < np; j += 32) {
       float sc = -INFINITY;
       if (j < n) {
-        const float* kr = sK + j * P;
-        const float* er = sE + (i - j + n - 1) * P;
+        const T_* kr = sK + j * P;
+        const T_* er = sE + (i - i0 - j + n - 1) * P;
         float dk = 0.f, de = 0.f;
         for (int d = 0; d < dh; ++d) {
-          dk = fmaf(q[d], kr[d], dk);
-          de = fmaf(q[d], er[d], de);
+          dk = fmaf(q[d], to_f32(kr[d]), dk);
+          de = fmaf(q[d], to_f32(er[d]), de);
         }
         sc = dk * scale + de * scale;
       }
@@ -91,7 +96,7 @@ conformer_attn_kernel(const T_* __restrict__ qkv, const float* __restrict__ rel,
     const float inv = 1.0f / sum;
     for (int d = lane; d < dh; d += 32) {
       float o = 0.f;
-      for (int j = 0; j < n; ++j) o = fmaf(pr[j], sV[j * dh + d], o);
+      for (int j = 0; j < n; ++j) o = fmaf(pr[j], to_f32(sV[j * dh + d]), o);
       out[((long long)b * n + i) * E + h * dh + d] = from_f32<T_>(o * inv);
     }
     __syncwarp();
@@ -102,8 +107,10 @@ template <typename T_>
 static int attn_launch(cudaStream_t s, const T_* qkv, const float* rel, T_* out, int B, int n, int heads, int dh) {
   RTDF_REQUIRE(qkv && rel && out && B > 0 && n > 0 && dh >= 1 && dh <= 64, "conformer_attention: bad arguments");
   const int np = (n + 31) & ~31;
-  const size_t smem = ((size_t)n * (dh + 1) + (size_t)n * dh + (size_t)(2 * n - 1) * (dh + 1) + 8 * 64 + 8 * np) * sizeof(float);
-  RTDF_REQUIRE(smem <= 220 * 1024, "conformer_attention: sequence of %d tokens too long", n);
+  const int P = dh + (sizeof(T_) == 2 ? 2 : 1);
+  const size_t smem = ((((size_t)n * P + (size_t)n * dh + (size_t)(n + 31) * P) * sizeof(T_) + 15) & ~(size_t)15) +
+                      ((size_t)8 * 64 + (size_t)8 * np) * sizeof(float);
+  RTDF_REQUIRE(smem <= 220 * 1024, "conformer_attention: sequence of %d tokens too long (bf16 mode: up to ~900, fp32: ~460)", n);
   RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&conformer_attn_kernel<T_>), (size_t)smem));
   dim3 grid(B * heads, ceil_div(n, 32));
   conformer_attn_kernel<T_><<<grid, 256, smem, s>>>(qkv, rel, out, n, heads, dh, 1.0f / sqrtf((float)dh));

@@ -77,7 +77,7 @@ def test_ragged_batches_preemphasis_determinism():
 
 def test_utterances_longer_than_one_attention_tile():
     """256 < T <= 512 frames (5.1 .. 10.2 s): the transformer's attention stays on tcgen05 (single 512-column TMEM buffer);
-    the AASIST back-end reaches 512 frames (10.2 s; 386 in fp32 mode), the Conformer ~400 (beyond that the call raises, see
+    the AASIST back-end reaches 512 frames (10.2 s; 386 in fp32 mode), the Conformer 512 as well (beyond that the call raises, see
     test_errors_are_loud)."""
     ec.check_e2e("My_XLSR_AASIST", "bf16", B=1, N=88000, num_layers=2, order="first")       # 5.5 s, T = 274
     ec.check_e2e("My_XLSR_AASIST", "bf16", B=2, N=119000, num_layers=2, order="first")      # 7.4 s, T = 371, T' = 123 nodes
@@ -85,6 +85,7 @@ def test_utterances_longer_than_one_attention_tile():
     ec.check_e2e("My_XLSR_AASIST", "bf16", B=2, N=164000, num_layers=2, order="first")      # 10.2 s, T = 512, T' = 170 nodes:
     # the transformer's single-buffer attention and the two-box conv slabs of the AASIST encoder at their limit
     ec.check_e2e("MyModel", "bf16", B=1, N=100000, num_layers=2, fixed_call=True)            # 6.25 s, T = 312
+    ec.check_e2e("MyModel", "bf16", B=2, N=164000, num_layers=2, fixed_call=True)            # 10.2 s, T = 512 (+ class token)
 
 
 def test_errors_are_loud():

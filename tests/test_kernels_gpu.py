@@ -127,7 +127,8 @@ def test_conformer_relpos_attention(is_bf16, impl):
 
 def test_conformer_attention_beyond_tensor_core_envelope():
     # n = 313 tokens: impl 1 (what the forward uses) switches to the SIMT kernel; impl 0 reports "unsupported"
-    kc.check_conformer_attention(is_bf16=1, impl=1, shapes=((1, 313, 4, 36),))
+    kc.check_conformer_attention(is_bf16=1, impl=1, shapes=((1, 313, 4, 36), (2, 513, 4, 36)))     # up to 10.2 s + class token
+    kc.check_conformer_attention(is_bf16=0, impl=1, shapes=((1, 400, 4, 36),))
     with pytest.raises(RuntimeError):
         kc.check_conformer_attention(is_bf16=1, impl=0, shapes=((1, 313, 4, 36),))
 

@@ -737,7 +737,7 @@ def check_conformer_attention(is_bf16=1, impl=0, shapes=((2, 50, 4, 36), (2, 200
         dots = torch.einsum("bhid,bhjd->bhij", q, k) * att.scale
         seq = torch.arange(n)
         dist = (seq[:, None] - seq[None, :]).clamp(-512, 512) + 512
-        rel = att.rel_pos_emb.weight[dist]
+        rel = att.rel_pos_emb.weight.detach()[dist]
         dots = dots + torch.einsum("bhnd,nrd->bhnr", q, rel) * att.scale
         ref = torch.einsum("bhij,bhjd->bhid", dots.softmax(-1), v).transpose(1, 2).reshape(B * n, E)
         dt = torch.bfloat16 if is_bf16 else torch.float32

@@ -161,3 +161,51 @@ def test_load_pretrained_fairseq_style_checkpoint(tmp_path, monkeypatch):
     torch.save({"model": {k: v for k, v in sd.items() if "layers.3." not in k}}, broken)
     with pytest.raises(RuntimeError, match="lacks XLS-R keys"):
         w2v.load_pretrained(skeleton, broken)
+
+
+def test_shard_and_batch_ranges_properties():
+    """Property test (hypothesis): for any utterance count, world size and batch size the shards partition [0, n) in order,
+    every shard but possibly trailing ones has ceil(n / W) items, and the batches of a shard tile it exactly with one ragged
+    batch at most (drop_last=False, reference main.py:200)."""
+    from hypothesis import given, settings, strategies as st
+    sc = pkg("scoring")
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(0, 200_000), world=st.integers(1, 8), batch=st.integers(1, 257))
+    def prop(n, world, batch):
+        pos = 0
+        per_ref = -(-n // world) if n else 0
+        for r in range(world):
+            lo, hi, per = sc.shard_range(n, r, world)
+            assert per == per_ref and lo == pos and lo <= hi <= n and hi - lo <= per
+            pos = hi
+            ranges = sc.batch_ranges(lo, hi, batch)
+            assert [a for a, _ in ranges] == list(range(lo, hi, batch))
+            assert all(0 < b - a <= batch for a, b in ranges)
+            assert sum(b - a for a, b in ranges) == hi - lo
+            assert sum(1 for a, b in ranges if b - a < batch) <= 1
+        assert pos == n
+
+    prop()
+    with pytest.raises(ValueError):
+        sc.shard_range(10, 2, 2)
+    with pytest.raises(ValueError):
+        sc.batch_ranges(0, 10, 0)
+
+
+def test_extractor_config_is_read_from_checkpoint_keys():
+    """XLS-R checkpoints carry per-conv LayerNorms and conv biases (extractor_mode=layer_norm); wav2vec2-base style ones a
+    GroupNorm after conv-0 and no conv bias (default).  The mirror classes build the matching parameter layout."""
+    w2v = pkg("models.wav2vec2_params")
+    fe = pkg("models.fe")
+    ln = w2v.Wav2Vec2Model(layers=1)
+    gn = w2v.Wav2Vec2Model(layers=1, extractor_mode="default", conv_bias=False)
+    assert w2v.extractor_config(ln.state_dict()) == ("layer_norm", True)
+    assert w2v.extractor_config(gn.state_dict()) == ("default", False)
+    assert "feature_extractor.conv_layers.0.2.weight" in gn.state_dict()           # GroupNorm affine
+    assert "feature_extractor.conv_layers.1.2.1.weight" not in gn.state_dict()     # no LayerNorm after conv-1
+    assert "feature_extractor.conv_layers.0.0.bias" not in gn.state_dict()
+    with pytest.raises(ValueError):
+        w2v.Wav2Vec2Model(layers=1, extractor_mode="group")
+    m = fe.My_XLSR_FE("cpu", num_layers=1, extractor_mode="default")
+    assert w2v.extractor_config(m.model.state_dict()) == ("default", False)

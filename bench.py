@@ -15,7 +15,7 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
             score vector -- identical at N = 1/2/4/8
   secondary BASELINE.json configs[1]: distilled student (6 layers) AASIST / Conformer at batch 256, utt/s (N = 1 only)
   latency   BASELINE.json configs[4]: p50 / p99 ms of single streaming-chunk calls (pinned host waveform -> host
-            score), XLSR-AASIST 1 s and 4 s, Conformer 1 s, batch 1 (N = 1 only)
+            score), XLSR-AASIST 1 s and 4 s at batch 1, 1 s at batch 8, Conformer 1 s at batch 1 (N = 1 only)
   roofline  dominant kernel (tcgen05 GEMM, 256-wide tiles): algorithmic FLOPs / CUDA-event time, vs the
             measured bf16 peak in MEASURED_PEAKS.json
   cpu_baseline  the reference forward timed on this box's host cores (bounded sample)
@@ -543,6 +543,8 @@ def run_b200(args):
         latency = {}
         latency["xlsr_aasist_b1_1s"] = latency_config(torch, model, 16000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], WEIGHT_BYTES_BF16)
         latency["xlsr_aasist_b1_4s"] = latency_config(torch, model, 64000, 1, device, n_warm, n_calls, peaks["hbm_gbs"], WEIGHT_BYTES_BF16)
+        latency["xlsr_aasist_b8_1s"] = latency_config(torch, model, 16000, 8, device, n_warm, max(100, n_calls // 2), peaks["hbm_gbs"],
+                                                      WEIGHT_BYTES_BF16)
         cb = importlib.import_module(PKG + ".models.conformer_baseline")
         torch.manual_seed(1024)
         conf = cb.Model("cpu", None).to(device).eval()

@@ -745,7 +745,11 @@ static int linear(const rtdf_ctx* c, cudaStream_t s, const void* A, long long ro
       // Streaming chunks (batch 1-8 x 49 frames, or one 4 s utterance): the GEMM is a weight-streaming problem, so
       // the tile count -- not the tile shape -- sets the time: 64-wide tiles give 4x the CTAs of the 256-wide ones
       // (the residual GEMMs of the transformer layers additionally split K, see run_frontend).
-      return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, 64, e);
+      // ... unless 64-wide tiles no longer fit one round of the persistent kernel (3 - 4 row tiles x a wide N): 128-wide
+      // tiles then finish in one round instead of two.
+      const long long row_tiles = (rows + 127) / 128;
+      const int width = (row_tiles * (L.n / 64) > kNumSMs && L.n % 128 == 0) ? 128 : 64;
+      return tc_gemm(s, plainA(A, rows, L.k), L.wb, L.n, L.k, TC_PLAIN, width, e);
     }
     if (variant == 2256 && !e.xb_out && !e.fold_stats && !e.rowln_counters && tail_split_enabled()) {
       // Wave quantisation: the persistent CTA-pair kernel walks ceil(tiles / 74) rounds of 256 x 256 tiles, and at the

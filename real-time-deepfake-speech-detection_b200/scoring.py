@@ -85,7 +85,8 @@ class ScoringPipeline:
         self.d2h_bytes = 0
 
     def push(self, host_batch):
-        """host_batch: (b, n_samples) fp32 CPU tensor, b <= batch_size; pinned memory makes the copy asynchronous."""
+        """host_batch: (b, n_samples) fp32 CPU tensor, b <= batch_size; pinned memory makes the copy asynchronous.
+        A CUDA tensor is accepted too and scored in place (no H2D)."""
         b = host_batch.shape[0]
         if b == 0:
             return
@@ -93,22 +94,27 @@ class ScoringPipeline:
             raise ValueError(f"batch shape {tuple(host_batch.shape)} does not fit ({self.batch_size}, {self.n_samples})")
         if self.count + b > self.scores_dev.numel():
             raise ValueError("ScoringPipeline capacity exceeded")
-        slot = self.step % len(self.dev_in)
-        self.step += 1
-        self.free[slot].synchronize()                    # the forward that read this slot has finished
-        x = self.dev_in[slot][:b]
-        with torch.cuda.stream(self.copy_stream):
-            x.copy_(host_batch, non_blocking=True)
-            self.ready[slot].record(self.copy_stream)
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(self.ready[slot])
-        logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef, regime=self.regime)
-        self.free[slot].record(cur)
+        if host_batch.is_cuda:
+            # already resident (e.g. synthesised on the device): no staging copy, plain stream order
+            x = host_batch.to(torch.float32).contiguous()
+            logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef, regime=self.regime)
+        else:
+            slot = self.step % len(self.dev_in)
+            self.step += 1
+            self.free[slot].synchronize()                    # the forward that read this slot has finished
+            x = self.dev_in[slot][:b]
+            with torch.cuda.stream(self.copy_stream):
+                x.copy_(host_batch, non_blocking=True)
+                self.ready[slot].record(self.copy_stream)
+            cur.wait_event(self.ready[slot])
+            logits = self.eng.forward(x, preemph=self.preemph, coef=self.coef, regime=self.regime)
+            self.free[slot].record(cur)
+            self.h2d_bytes += host_batch.numel() * 4
         dst = self.scores_dev[self.count:self.count + b]
         dst.copy_(logits[:, 1])                                                          # stays on the device ...
         self.scores_host[self.count:self.count + b].copy_(dst, non_blocking=True)       # ... and goes home asynchronously
         self.count += b
-        self.h2d_bytes += host_batch.numel() * 4
         self.d2h_bytes += b * 4
 
     def device_scores(self):

@@ -180,6 +180,8 @@ def test_scoring_pipeline_matches_direct_forward_bit_exactly():
         out.copy_(x[lo:hi])
     all_scores = scoring.score_utterances(prod, 11, load, N, B, "cuda")
     assert torch.equal(all_scores.cpu(), want)
+    on_dev = scoring.score_utterances(prod, 11, lambda lo, hi, out: x[lo:hi].cuda(), N, 5, "cuda", zero_copy=True)  # resident batches
+    assert torch.equal(on_dev.cpu(), want)
     pool = x.pin_memory()
     zero_copy = scoring.score_utterances(prod, 11, lambda lo, hi, out: pool[lo:hi], N, 3, "cuda", zero_copy=True)   # other batch size
     assert torch.equal(zero_copy.cpu(), want)

@@ -220,13 +220,19 @@ def synth_on_device(torch, batch, n, seed, device):
     return x.clamp_(-1, 1).contiguous()
 
 
+def sweep_tone(torch, n, device):
+    """The 220 Hz component of every sweep utterance -- ONE definition, so that the pinned-pool path and the on-device path
+    synthesise bit-identical waveforms."""
+    t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
+    return 0.05 * torch.sin(2 * torch.pi * 220.0 * t)
+
+
 def sweep_utterances_to_host(torch, lo, hi, n, device):
     """Utterances [lo, hi) of the fixed sweep set, each a function of its GLOBAL index only (Philox stream seeded with
     SWEEP_SEED + index), generated on the device and parked in pinned host memory (the DataLoader's role)."""
     pool = torch.empty(max(hi - lo, 1), n, dtype=torch.float32).pin_memory()
     g = torch.Generator(device=device)
-    t = torch.arange(n, device=device, dtype=torch.float32) / 16000.0
-    tone = 0.05 * torch.sin(2 * torch.pi * 220.0 * t)
+    tone = sweep_tone(torch, n, device)
     chunk = 256
     for c0 in range(lo, hi, chunk):
         c1 = min(c0 + chunk, hi)
@@ -495,7 +501,7 @@ def run_b200(args):
         if on_device:                                  # would be 46 GB) are synthesised per batch on the device instead
             pool = None
             gen = torch.Generator(device=device)
-            tone = 0.05 * torch.sin(2 * torch.pi * 220.0 * torch.arange(N, device=device, dtype=torch.float32) / 16000.0)
+            tone = sweep_tone(torch, N, device)
 
             def load_batch(b_lo, b_hi, out):
                 buf = torch.empty(b_hi - b_lo, N, dtype=torch.float32, device=device)

@@ -189,6 +189,7 @@ struct AttWsParams {
   // softmax warpgroup works, K / V arrive as two 256-row boxes (rows past T zero-filled by TMA), S = two N <= 256 MMAs
   // per k-step, O sits at column 448 (S columns consumed before P V is issued; P covers [0, Tk/2 <= 256)).
   int n_buf, buf_cols, o_col, kv_boxes;
+  int eager_issue; // MMA thread issues whichever of (P V of the older tile, S of the next tile) is ready first (RTDF_ATTN_EAGER)
   int reverse;     // items from the last utterance to the first (the rows the QKV projection wrote last are still in L2)
   // RTDF_ATTN_DEBUG bit mask -- timing experiments only, the output is wrong when any bit is set (tools/attention_experiment.py):
   // 1 = no row-max pass, 2 = exp pass on the first chunk only, 4 = no TMA loads, 8 = no S MMAs, 16 = no PV MMAs, 32 = no O store
@@ -285,10 +286,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         mma_commit(empty_bar(s));     // Q, K, V of this stage are no longer read
         mma_commit(ofull_bar(g));
       };
-      for (int i = 0; i < n_local; ++i) {
+      auto issue_s = [&](int i) {
         const int g = i % nb, s = i % p.n_stages;
-        mbar_wait(tempty_bar(g), ((i / nb) & 1) ^ 1);   // warpgroup g has read O of item i - n_buf
-        mbar_wait(full_bar(s), (i / p.n_stages) & 1);
         tc_fence_after();
         const uint32_t sQ = base + s * p.stage_bytes, sK = sQ + 16384;
 #pragma unroll
@@ -300,10 +299,47 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                           idesc_s2, k != 0);
           }
         mma_commit(sfull_bar(g));
-        if (nb == 1) issue_pv(i);          // single buffer: S(i+1) has to wait for O(i) anyway
-        else if (i > 0) issue_pv(i - 1);   // ping-pong: S(i) is issued ahead of P V(i-1)
+      };
+      if (nb == 2 && p.eager_issue) {
+        // Event-driven issue order: the thread polls what each buffer is waiting for and issues whichever is ready -- the
+        // P V of the older tile as soon as its probabilities are in tensor memory, the S of the next tile as soon as its
+        // buffer's O has been read and its stage has landed -- instead of blocking on one barrier while the other
+        // buffer's work is ready (head-of-line blocking of the fixed S(i), P V(i-1) order).
+        int next_s = 0, next_pv = 0;
+        while (next_pv < n_local) {
+          bool progressed = false;
+          if (next_pv < next_s && mbar_test_wait(pfull_bar(next_pv & 1), (next_pv >> 1) & 1)) {
+            const int j = next_pv, g = j & 1, s = j % p.n_stages;
+            tc_fence_after();
+            const uint32_t sV = base + s * p.stage_bytes + 16384 + p.kv_bytes;
+            const uint32_t tP = tmem + g * kBufCols, tO = tP + kOCol;
+            for (int ks = 0; ks < ksteps && !(p.debug & 16); ++ks)
+              mma_bf16_ts(tO, tP + ks * 8, umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
+            mma_commit(empty_bar(s));
+            mma_commit(ofull_bar(g));
+            ++next_pv;
+            progressed = true;
+          }
+          if (next_s < n_local && next_s - next_pv < 2 &&
+              mbar_test_wait(tempty_bar(next_s & 1), ((next_s >> 1) & 1) ^ 1) &&
+              mbar_test_wait(full_bar(next_s % p.n_stages), (next_s / p.n_stages) & 1)) {
+            issue_s(next_s);
+            ++next_s;
+            progressed = true;
+          }
+          (void)progressed;
+        }
+      } else {
+        for (int i = 0; i < n_local; ++i) {
+          const int g = i % nb, s = i % p.n_stages;
+          mbar_wait(tempty_bar(g), ((i / nb) & 1) ^ 1);   // warpgroup g has read O of item i - n_buf
+          mbar_wait(full_bar(s), (i / p.n_stages) & 1);
+          issue_s(i);
+          if (nb == 1) issue_pv(i);          // single buffer: S(i+1) has to wait for O(i) anyway
+          else if (i > 0) issue_pv(i - 1);   // ping-pong: S(i) is issued ahead of P V(i-1)
+        }
+        if (nb == 2 && n_local > 0) issue_pv(n_local - 1);
       }
-      if (nb == 2 && n_local > 0) issue_pv(n_local - 1);
       pdl_launch_dependents();
     }
   } else {
@@ -449,6 +485,14 @@ int attention_ws(cudaStream_t s, const bf16* qkv, bf16* ctx, int B, int T, int H
   p.T = T;
   p.H = H;
   p.reverse = reverse ? 1 : 0;
+  {
+    static int eager = -1;
+    if (eager < 0) {
+      const char* e = getenv("RTDF_ATTN_EAGER");
+      eager = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.eager_issue = eager;
+  }
   p.Tk = (T + 15) & ~15;
   p.n_qt = ceil_div(T, 128);
   const long long items = (long long)B * H * p.n_qt;

@@ -1004,6 +1004,28 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     return linear(c, s, A, M, L, e);
   };
   const size_t n_layers = c->layers.size();
+  if (c->layer_stack && c->stack_layers && !layer_taps && skinny_rows(c, M) && M <= kStackMaxRows && w.partials) {
+    // <= 64 frames in flight (batch 1 x 1 s): all layers + the final LayerNorm in one persistent kernel
+    StackParams sp;
+    sp.layers = c->stack_layers;
+    sp.n_layers = (int)n_layers;
+    sp.R = (int)M;
+    sp.B = B;
+    sp.T = T;
+    sp.x = w.x;
+    sp.xn = static_cast<bf16*>(w.xb);
+    sp.qkv = static_cast<bf16*>(w.qkv);
+    sp.att = static_cast<bf16*>(w.attn);
+    sp.h = static_cast<bf16*>(w.hbuf);
+    sp.part = w.partials;
+    sp.feats = feats;
+    sp.gF = c->enc_ln.g;
+    sp.bF = c->enc_ln.b;
+    sp.wmaps = c->stack_wmaps;
+    sp.sync = c->stack_sync;
+    sp.fault = c->stack_fault;
+    return layer_stack_bf16(s, sp);
+  }
   const size_t tap_bytes = (size_t)M * 1024 * sizeof(float);
   if (layer_taps) RTDF_CHECK_CUDA(cudaMemcpyAsync(layer_taps, w.x, tap_bytes, cudaMemcpyDeviceToDevice, s));
   if (fold) RTDF_TRY(cast_stats_rows(s, w.x, nullptr, 0, M, static_cast<bf16*>(w.xb), w.stats));   // x after the pos-conv
@@ -1431,6 +1453,10 @@ int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc) {
     const char* e = getenv("RTDF_LN_FOLD");
     c->ln_fold = e && e[0] == '1' && c->d.precision == RTDF_PREC_BF16;
   }
+  {  // RTDF_LAYER_STACK=0: streaming chunks of <= 64 frames keep the kernel-per-op chain instead of the persistent layer-stack kernel
+    const char* e = getenv("RTDF_LAYER_STACK");
+    c->layer_stack = !(e && e[0] == '0') && c->d.precision == RTDF_PREC_BF16 && !c->ln_fold;
+  }
   {  // second stream + fork / join events for the independent graph branches of the AASIST back-end (RTDF_BRANCH_STREAMS=0: off)
     const char* e = getenv("RTDF_BRANCH_STREAMS");
     if (!(e && e[0] == '0') && c->d.backend == RTDF_BACKEND_AASIST) {
@@ -1492,6 +1518,39 @@ int rtdf_finalize(rtdf_ctx* c) {
   RTDF_TRY(pack_xlsr(c));
   if (c->d.backend == RTDF_BACKEND_AASIST) RTDF_TRY(pack_aasist(c));
   if (c->d.backend == RTDF_BACKEND_CONFORMER) RTDF_TRY(pack_conformer(c));
+  if (c->layer_stack) {
+    std::vector<rtdf::StackLayer> host;
+    for (const XlsrLayer& L : c->layers) {
+      rtdf::StackLayer sl;
+      sl.wqkv = L.qkv.wb; sl.wo = L.out.wb; sl.w1 = L.fc1.wb; sl.w2 = L.fc2.wb;
+      sl.bqkv = L.qkv.b; sl.bo = L.out.b; sl.b1 = L.fc1.b; sl.b2 = L.fc2.b;
+      sl.g1 = L.ln1.g; sl.be1 = L.ln1.b; sl.g2 = L.ln2.g; sl.be2 = L.ln2.b;
+      host.push_back(sl);
+    }
+    void* dev = nullptr;
+    RTDF_CHECK_CUDA(cudaMalloc(&dev, host.size() * sizeof(rtdf::StackLayer) + 256));
+    c->owned.push_back(dev);
+    RTDF_CHECK_CUDA(cudaMemcpy(dev, host.data(), host.size() * sizeof(rtdf::StackLayer), cudaMemcpyHostToDevice));
+    c->stack_layers = static_cast<rtdf::StackLayer*>(dev);
+    {
+      std::vector<CUtensorMap> maps(4 * host.size());
+      RTDF_TRY(rtdf::layer_stack_build_wmaps(host.data(), (int)host.size(), maps.data()));
+      void* dm = nullptr;
+      RTDF_CHECK_CUDA(cudaMalloc(&dm, maps.size() * sizeof(CUtensorMap)));
+      c->owned.push_back(dm);
+      RTDF_CHECK_CUDA(cudaMemcpy(dm, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+      c->stack_wmaps = static_cast<CUtensorMap*>(dm);
+    }
+    void* words = nullptr;
+    RTDF_CHECK_CUDA(cudaMalloc(&words, 256));
+    c->owned.push_back(words);
+    RTDF_CHECK_CUDA(cudaMemset(words, 0, 256));
+    c->stack_sync = static_cast<unsigned*>(words);
+    void* flag = nullptr;
+    RTDF_CHECK_CUDA(cudaHostAlloc(&flag, sizeof(int), cudaHostAllocMapped));
+    c->stack_fault = static_cast<int*>(flag);
+    *c->stack_fault = 0;
+  }
   RTDF_CHECK_CUDA(cudaDeviceSynchronize());
   if (!c->scratch.empty()) {   // bf16 mode: release the fp32 sources of the packed GEMM weights
     std::set<void*> dead(c->scratch.begin(), c->scratch.end());
@@ -1513,6 +1572,7 @@ void rtdf_destroy(rtdf_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   for (void* p : c->owned) cudaFree(p);
+  if (c->stack_fault) cudaFreeHost(c->stack_fault);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -1537,6 +1597,11 @@ static int check_ready(const rtdf_ctx* c) {
   RTDF_REQUIRE(c, "null context");
   if (!c->finalized) {
     rtdf::set_error("context not finalized: call rtdf_finalize() after loading the weights");
+    return RTDF_ERR_STATE;
+  }
+  if (c->stack_fault && *static_cast<volatile int*>(c->stack_fault)) {
+    rtdf::set_error("an earlier forward failed: the layer-stack kernel timed out at a grid barrier (its 128 CTAs were not "
+                    "co-resident); results since then are invalid.  RTDF_LAYER_STACK=0 selects the kernel-per-op chain");
     return RTDF_ERR_STATE;
   }
   return RTDF_OK;

@@ -1,5 +1,6 @@
 // Model context: weight store, packed weights, workspace plan, forward orchestration.
 #pragma once
+#include "layer_stack.cuh"
 #include <map>
 #include <string>
 #include <vector>
@@ -128,6 +129,12 @@ struct rtdf_ctx {
   rtdf::Lin pos;      // packed [1024][8192]
   std::vector<rtdf::XlsrLayer> layers;
   rtdf::Norm enc_ln;
+  // streaming chunks of <= 64 frames (bf16): the transformer layers as one persistent kernel (layer_stack.cu)
+  bool layer_stack = false;                  // RTDF_LAYER_STACK (read at rtdf_create)
+  rtdf::StackLayer* stack_layers = nullptr;  // device array of per-layer pointers (built by rtdf_finalize)
+  CUtensorMap* stack_wmaps = nullptr;        // device array [layers][4] of weight tensor maps
+  unsigned* stack_sync = nullptr;            // its grid-barrier words
+  int* stack_fault = nullptr;                // mapped host word the kernel sets when a barrier times out
   rtdf::AasistW aasist;
   rtdf::ConformerW conf;
 };

@@ -155,3 +155,40 @@ def check_timed_configuration(B=64, N=64000, rows=(0, 31, 63), pair=2):
     again = eng.forward(xd, regime="throughput").cpu()
     assert torch.equal(again, big), "forward at the timed batch is not deterministic"
     return res
+
+
+def check_layer_stack():
+    """Streaming chunks of <= 64 frames in flight (bf16): the transformer layers run as ONE persistent kernel
+    (csrc/layer_stack.cu; 128 CTAs, grid barriers between the phases).  Checked against the CPU oracle at the usual
+    tolerances, against the kernel-per-op chain (RTDF_LAYER_STACK=0), for row counts that fill 1..4 m-tiles with and
+    without a ragged last tile and several utterances per call, and by its launch count (so a silent fall-back to the
+    chain fails the test).  Replays must be bit-identical (fixed summation order everywhere)."""
+    from tests.util import native
+    lib = native().load()
+    out = {}
+    out["aasist_b1_1s"] = check_e2e("XLSR_AASIST", "bf16", B=1, N=16000)                 # 24 layers, 49 rows
+    out["conformer_b1_1s"] = check_e2e("ConformerModel", "bf16", B=1, N=16000)
+    for B, N in ((2, 8000), (4, 5200), (1, 20800), (3, 3000), (1, 1000)):                  # 48, 64, 64, 27, 2 rows
+        out[f"feats_b{B}_n{N}"] = check_frontend_block("bf16", B=B, N=N, kind="My_XLSR_AASIST", num_layers=3, order="first")
+    # same model through both paths
+    os.environ["RTDF_LAYER_STACK"] = "0"
+    try:
+        _, chain = build_pair("My_XLSR_AASIST", "bf16", num_layers=4, order="first")
+        chain.engine()
+    finally:
+        del os.environ["RTDF_LAYER_STACK"]
+    _, stack = build_pair("My_XLSR_AASIST", "bf16", num_layers=4, order="first")
+    stack.engine()
+    x = _waves(1, 16000, seed=11).cuda()
+    n0 = lib.rtdf_launch_count()
+    a = stack(x).clone()
+    n1 = lib.rtdf_launch_count()
+    b = chain(x).clone()
+    n2 = lib.rtdf_launch_count()
+    out["launches_stack"], out["launches_chain"] = int(n1 - n0), int(n2 - n1)
+    out["stack_vs_chain"] = float((a - b).abs().max())
+    assert out["launches_chain"] - out["launches_stack"] >= 4 * 6, out      # >= 7 kernels per layer replaced by one launch
+    assert out["stack_vs_chain"] <= TOL["bf16"], out
+    for _ in range(5):
+        assert torch.equal(stack(x), a), "layer-stack replays differ"
+    return out

@@ -53,6 +53,10 @@ def test_timed_configuration_parity_and_batch_invariance():
     ec.check_timed_configuration()
 
 
+def test_layer_stack_kernel_streaming_chunks():
+    ec.check_layer_stack()
+
+
 def test_folded_layernorm_mode(monkeypatch):
     """RTDF_LN_FOLD=1 (opt-in): no LayerNorm kernels in the transformer layers -- the projections apply the normalisation
     in their epilogues from per-row statistics the residual GEMMs emit.  Same tolerances as the default path, in the

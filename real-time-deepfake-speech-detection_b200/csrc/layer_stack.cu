@@ -557,12 +557,13 @@ __device__ __forceinline__ void attention_phase_mma(const StackParams& p, unsign
 // =====================================================================================================================
 constexpr int kTcABytes = 16 * 8192;                   // 16 k-chunks x (64 rows x 128 B)
 constexpr int kTcWBytes = 16 * 32 * 128;               // 16 k-chunks x (32 rows x 128 B)
+constexpr int kTcIssuers = 8;                          // MMA-issuing threads per GEMM phase (measured: profiles/r02_layer_stack.txt)
 constexpr int kTcSmemBytes = kTcABytes + kTcWBytes + 8192 /* M = 128 reads 8 KB past the last A chunk: keep it inside */ + 1024;
 
 struct TcState {
   uint32_t sA, sW;             // shared-memory addresses (1024-byte aligned)
-  uint32_t abar, wbar, dbar;   // mbarriers: A landed, W landed, MMAs retired
-  uint32_t tmem;               // accumulator base (32 columns)
+  uint32_t abar, wbar, dbar;   // mbarriers: A landed (one per issuer, 8 bytes apart), W landed, MMAs retired (count = issuers)
+  uint32_t tmem;               // accumulator base (32 columns per issuer)
   uint32_t pa, pw, pd;         // their phase parities (uniform over the CTA)
 };
 
@@ -582,33 +583,39 @@ template <int N, class Epi>
 __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* mapA, int k0, int R, const float* __restrict__ bias,
                                               int flags, unsigned long long* tr, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 16) {   // one A box (k-chunk) per lane
+  constexpr int ni = kTcIssuers, per = 16 / ni;   // MMA issuers, k-chunks per issuer
+  if (threadIdx.x < 16) {   // one A box (k-chunk) per lane; the chunks of issuer i complete on mbarrier abar + 8 i
     if (tr && threadIdx.x == 0) tr[0] = clock64();
     // the rows were written by other CTAs' generic-proxy stores and are ordered before this point by the grid barrier; the
     // proxy fence orders them before the async-proxy (TMA) reads below
     // (restricted to the global space: the unrestricted form costs 800 cycles more per phase, profiles/r02_layer_stack.txt)
     if (!(flags & 1)) asm volatile("fence.proxy.async.global;" ::: "memory");
-    if (threadIdx.x == 0) ptx::mbar_expect_tx(st.abar, (uint32_t)kTcABytes);
+    const uint32_t mybar = st.abar + 8 * (threadIdx.x / per);
+    if (threadIdx.x % per == 0) ptx::mbar_expect_tx(mybar, (uint32_t)per * 8192u);
     __syncwarp(0xffffu);
-    ptx::tma_load_2d(st.sA + threadIdx.x * 8192, mapA, st.abar, k0 + threadIdx.x * 64, 0);
+    ptx::tma_load_2d(st.sA + threadIdx.x * 8192, mapA, mybar, k0 + threadIdx.x * 64, 0);
     if (tr && threadIdx.x == 0) tr[1] = clock64();
   }
-  if (threadIdx.x == 64) {   // MMA issuer: warp 2, lane 0.  Descriptors advance by plain additions to the address field
-    ptx::mbar_wait(st.wbar, st.pw);   // (addresses < 256 KB: no carry out of its 14 bits)
-    if (tr) tr[2] = clock64();
-    ptx::mbar_wait(st.abar, st.pa);
-    if (tr) tr[3] = clock64();
-    ptx::tc_fence_after();
+  // MMA issuers: lane 0 of warps 0 .. ni-1, each over its own k-chunks into its own accumulator (columns 32 i ..): one thread
+  // issues an N = 32 MMA every ~50 cycles, the tensor pipe takes them faster.  Descriptors advance by plain additions to the
+  // address field (addresses < 256 KB: no carry out of its 14 bits)
+  if (lane == 0 && warp < ni) {
+    ptx::mbar_wait(st.wbar, st.pw);
+    if (tr && warp == 0) tr[2] = clock64();
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, N);
     const uint64_t adesc = ptx::umma_desc_sw128(st.sA), bdesc = ptx::umma_desc_sw128(st.sW);
+    ptx::mbar_wait(st.abar + 8 * warp, st.pa);
+    if (tr && warp == ni - 1) tr[3] = clock64();
+    ptx::tc_fence_after();
+    const uint64_t abase = adesc + (uint64_t)((warp * per * 8192) >> 4), bbase = bdesc + (uint64_t)((warp * per * N * 128) >> 4);
 #pragma unroll
-    for (int c = 0; c < 16; ++c)
+    for (int j = 0; j < per; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        ptx::mma_bf16_ss(st.tmem, adesc + (uint64_t)((c * 8192 + k * 32) >> 4), bdesc + (uint64_t)((c * N * 128 + k * 32) >> 4), idesc,
-                         (c | k) != 0);
+        ptx::mma_bf16_ss(st.tmem + 32 * warp, abase + (uint64_t)((j * 8192 + k * 32) >> 4), bbase + (uint64_t)((j * N * 128 + k * 32) >> 4),
+                         idesc, (j | k) != 0);
     ptx::mma_commit(st.dbar);
-    if (tr) tr[4] = clock64();
+    if (tr && warp == 0) tr[4] = clock64();
   }
   // read-back: TMEM lane quarter = warp % 4 (rows 0-31 / 32-63), 16 columns per warp (N = 32: warps 0, 1, 4, 5; N = 16: warps 0, 1)
   // (M = 64 MMAs -- accumulator row r at lane 32 (r / 16) + r % 16 -- were tried: same 47 cycles per MMA)
@@ -632,6 +639,13 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
       v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4[i].y;
       v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4[i].z;
       v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4[i].w;
+    }
+#pragma unroll
+    for (int a = 1; a < ni; ++a) {   // the other issuers' accumulators, in order
+      ptx::tmem_ld16(st.tmem + (static_cast<uint32_t>(q * 32) << 16) + 32 * a + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
     }
     if (row < R) epi(row, c0, v);
     ptx::tc_fence_before();
@@ -672,7 +686,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
   __shared__ float s_red[2 * kWarps];
   __shared__ int s_abort;
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) unsigned long long s_bars[3];
+  __shared__ __align__(8) unsigned long long s_bars[10];
   const int cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
   const int R = p.R;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -680,21 +694,21 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
   st.sA = ptx::smem_u32(smem);
   st.sW = st.sA + kTcABytes;
   st.abar = ptx::smem_u32(&s_bars[0]);
-  st.wbar = ptx::smem_u32(&s_bars[1]);
-  st.dbar = ptx::smem_u32(&s_bars[2]);
+  st.wbar = ptx::smem_u32(&s_bars[8]);
+  st.dbar = ptx::smem_u32(&s_bars[9]);
   st.pa = st.pw = st.pd = 0;
   if (tid == 0) {
     s_abort = 0;
-    ptx::mbar_init(st.abar, 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(st.abar + 8 * i, 1);
     ptx::mbar_init(st.wbar, 1);
-    ptx::mbar_init(st.dbar, 1);
+    ptx::mbar_init(st.dbar, kTcIssuers);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&map_xn);
     ptx::prefetch_tmap(&map_att);
     ptx::prefetch_tmap(&map_h);
   }
   if (warp == 3) {
-    ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 32);
+    ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 256);
     ptx::tmem_relinquish();
   }
   // the 8 KB behind the last A chunk are read (never used) by the M = 128 MMAs: give them defined contents once
@@ -715,7 +729,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     const bool last = l + 1 == p.n_layers;
     // ---- q, k, v = LN1(x) Wqkv^T + b: 32 columns per CTA, 96 CTAs
     STAMP(0);
-    TC_BARRIER(if (qkv_cta) tc_issue_w<32>(st, wm + 4 * l + 0, 0, cta * 32));
+    TC_BARRIER(if (qkv_cta) tc_issue_w<32>(st, wm + 4 * l + 0, 0, cta * 32); if (tid == 0) ptx::prefetch_tmap(&map_xn));
     STAMP(1);
     if (qkv_cta)
       tc_gemm_phase<32>(st, &map_xn, 0, R, W.bqkv + cta * 32, p.flags, TR(0), [&](int row, int c0, const float (&v)[16]) {
@@ -727,7 +741,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     attention_phase_mma(p, smem, TR(4));
     STAMP(6);
     // ---- attention output projection: 16 columns per CTA, 64 CTAs, partial slot 0 (bias / residual: LayerNorm phase)
-    TC_BARRIER(if (out_cta) tc_issue_w<16>(st, wm + 4 * l + 1, 0, cta * 16));
+    TC_BARRIER(if (out_cta) tc_issue_w<16>(st, wm + 4 * l + 1, 0, cta * 16); if (tid == 0) ptx::prefetch_tmap(&map_att));
     STAMP(7);
     if (out_cta)
       tc_gemm_phase<16>(st, &map_att, 0, R, nullptr, p.flags, TR(1), [&](int row, int c0, const float (&v)[16]) {
@@ -739,7 +753,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     if (cta < R) ln_row(p, cta, W.bo, 1, W.g2, W.be2, true, p.xn, nullptr, s_red);
     STAMP(12);
     // ---- h = GELU(LN2(x) W1^T + b1): 32 columns per CTA
-    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 2, 0, cta * 32));
+    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 2, 0, cta * 32); if (tid == 0) ptx::prefetch_tmap(&map_xn));
     STAMP(13);
     tc_gemm_phase<32>(st, &map_xn, 0, R, W.b1 + cta * 32, p.flags, TR(2), [&](int row, int c0, const float (&v)[16]) {
       float y[16];
@@ -753,7 +767,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     });
     STAMP(16);
     // ---- fc2: 32 columns x one quarter of K = 4096 per CTA, partial slot = K quarter
-    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 3, (cta >> 5) * 1024, (cta & 31) * 32));
+    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 3, (cta >> 5) * 1024, (cta & 31) * 32); if (tid == 0) ptx::prefetch_tmap(&map_h));
     STAMP(17);
     tc_gemm_phase<32>(st, &map_h, (cta >> 5) * 1024, R, nullptr, p.flags, TR(3), [&](int row, int c0, const float (&v)[16]) {
       store16_f32(p.part + ((size_t)(cta >> 5) * R + row) * 1024 + (cta & 31) * 32 + c0, v);
@@ -781,7 +795,7 @@ finish:
   __syncthreads();
   if (warp == 3) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(st.tmem, 32);
+    ptx::tmem_dealloc(st.tmem, 256);
   }
 }
 

@@ -171,15 +171,20 @@ __device__ __forceinline__ void reduce_phase(const float (&acc)[4][NT][4], float
 
 // ---- LayerNorm phase: one row per CTA ------------------------------------------------------------------------------------
 // v = x[row] (+ bias + sum of np partials, in order); x[row] = v (if write_x); LayerNorm(v) -> xn (bf16) or feats (fp32)
-__device__ __forceinline__ void ln_row(const StackParams& p, int row, const float* __restrict__ bias, int np,
-                                       const float* __restrict__ gam, const float* __restrict__ bet, bool write_x, bf16* xn_out,
+struct LnWeights { float4 bias, g, b; };   // this thread's 4 columns of the projection bias and the LayerNorm affine
+__device__ __forceinline__ LnWeights ln_weights(const float* __restrict__ bias, const float* __restrict__ gam, const float* __restrict__ bet) {
+  const int c = threadIdx.x * 4;
+  LnWeights w;
+  w.bias = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  w.g = __ldg(reinterpret_cast<const float4*>(gam + c));
+  w.b = __ldg(reinterpret_cast<const float4*>(bet + c));
+  return w;
+}
+__device__ __forceinline__ void ln_row(const StackParams& p, int row, const LnWeights& lw, int np, bool write_x, bf16* xn_out,
                                        float* f_out, float* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = tid * 4;
   float4 v = __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)row * 1024 + c));
-  if (bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
+  v.x += lw.bias.x; v.y += lw.bias.y; v.z += lw.bias.z; v.w += lw.bias.w;
   for (int q = 0; q < np; ++q) {
     const float4 a = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)q * p.R + row) * 1024 + c));
     v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
@@ -199,7 +204,7 @@ __device__ __forceinline__ void ln_row(const StackParams& p, int row, const floa
 #pragma unroll
   for (int w = 0; w < kWarps; ++w) var += s_red[kWarps + w];
   const float rstd = rsqrtf(var * (1.0f / 1024.0f) + 1e-5f);
-  const float4 gg = __ldg(reinterpret_cast<const float4*>(gam + c)), bb = __ldg(reinterpret_cast<const float4*>(bet + c));
+  const float4 gg = lw.g, bb = lw.b;
   const float y0 = dx * rstd * gg.x + bb.x, y1 = dy * rstd * gg.y + bb.y, y2 = dz * rstd * gg.z + bb.z, y3 = dw * rstd * gg.w + bb.w;
   if (write_x) __stcg(reinterpret_cast<float4*>(p.x + (size_t)row * 1024 + c), v);
   if (xn_out) {
@@ -209,6 +214,12 @@ __device__ __forceinline__ void ln_row(const StackParams& p, int row, const floa
     __stcg(reinterpret_cast<uint2*>(xn_out + (size_t)row * 1024 + c), o);
   }
   if (f_out) __stcg(reinterpret_cast<float4*>(f_out + (size_t)row * 1024 + c), make_float4(y0, y1, y2, y3));
+}
+
+__device__ __forceinline__ void ln_row(const StackParams& p, int row, const float* __restrict__ bias, int np,
+                                       const float* __restrict__ gam, const float* __restrict__ bet, bool write_x, bf16* xn_out,
+                                       float* f_out, float* s_red) {
+  ln_row(p, row, ln_weights(bias, gam, bet), np, write_x, xn_out, f_out, s_red);
 }
 
 // ---- attention phase (<= 64 keys per utterance): fp32 SIMT ------------------------------------------------------------------
@@ -550,15 +561,15 @@ __device__ __forceinline__ void attention_phase_mma(const StackParams& p, unsign
 // tcgen05 variant (default): the GEMM phases on the 5th-generation tensor cores.
 //   A (<= 64 rows x 1024, bf16) arrives as 16 TMA boxes of 64 rows x 64 columns (128-byte swizzled rows; rows >= R are
 //   zero-filled by the TMA unit), the CTA's weight slice (32 or 16 rows x 1024) as 16 boxes issued one grid barrier EARLIER
-//   (between the arrive and wait halves), so the HBM stream runs under the barrier and the A load.  One thread issues the 64
-//   MMAs (M = 128: the upper 64 rows of every A tile alias the next tile -- their products land in accumulator rows nobody
-//   reads), the accumulator (128 lanes x 32 columns of tensor memory) is read back by two or four warps: no K split across
-//   warps, no cross-warp reduction, no weight registers.
+//   or one whole phase earlier), so the HBM stream runs under the barrier / the attention or LayerNorm phase.  Eight threads
+//   issue 8 MMAs each (M = 64, N = 32 | 16, K = 16) over their own two k-chunks into their own accumulator (32 columns of
+//   tensor memory each) -- a single thread paces such small MMAs at ~50 cycles apiece, the tensor pipe takes them at ~24 --
+//   and the read-back sums the eight accumulators in order: no weight registers, no shared-memory reduction.
 // =====================================================================================================================
 constexpr int kTcABytes = 16 * 8192;                   // 16 k-chunks x (64 rows x 128 B)
 constexpr int kTcWBytes = 16 * 32 * 128;               // 16 k-chunks x (32 rows x 128 B)
 constexpr int kTcIssuers = 8;                          // MMA-issuing threads per GEMM phase (measured: profiles/r02_layer_stack.txt)
-constexpr int kTcSmemBytes = kTcABytes + kTcWBytes + 8192 /* M = 128 reads 8 KB past the last A chunk: keep it inside */ + 1024;
+constexpr int kTcSmemBytes = kTcABytes + kTcWBytes + 1024;   // + slack for the 1024-byte alignment of the tiles
 
 struct TcState {
   uint32_t sA, sW;             // shared-memory addresses (1024-byte aligned)
@@ -579,9 +590,10 @@ __device__ __forceinline__ void tc_issue_w(const TcState& st, const CUtensorMap*
 
 // one GEMM phase of a participating CTA: A boxes, MMAs, accumulator read-back.  epi(row, first column, 16 fp32 values + bias);
 // bias (nullable) points at the CTA's first column and is fetched before the accumulator is ready.
-template <int N, class Epi>
+// after_mma(): runs in warp 0 once this phase's MMAs have retired (the weight buffer is free again), ahead of the read-back.
+template <int N, class Epi, class After>
 __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* mapA, int k0, int R, const float* __restrict__ bias,
-                                              int flags, unsigned long long* tr, Epi epi) {
+                                              int flags, unsigned long long* tr, Epi epi, After after_mma) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ni = kTcIssuers, per = 16 / ni;   // MMA issuers, k-chunks per issuer
   if (threadIdx.x < 16) {   // one A box (k-chunk) per lane; the chunks of issuer i complete on mbarrier abar + 8 i
@@ -602,7 +614,7 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
   if (lane == 0 && warp < ni) {
     ptx::mbar_wait(st.wbar, st.pw);
     if (tr && warp == 0) tr[2] = clock64();
-    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, N);
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(64, N);
     const uint64_t adesc = ptx::umma_desc_sw128(st.sA), bdesc = ptx::umma_desc_sw128(st.sW);
     ptx::mbar_wait(st.abar + 8 * warp, st.pa);
     if (tr && warp == ni - 1) tr[3] = clock64();
@@ -617,10 +629,12 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
     ptx::mma_commit(st.dbar);
     if (tr && warp == 0) tr[4] = clock64();
   }
-  // read-back: TMEM lane quarter = warp % 4 (rows 0-31 / 32-63), 16 columns per warp (N = 32: warps 0, 1, 4, 5; N = 16: warps 0, 1)
-  // (M = 64 MMAs -- accumulator row r at lane 32 (r / 16) + r % 16 -- were tried: same 47 cycles per MMA)
-  const int q = warp & 3, c0 = N == 32 ? (warp >> 2) * 16 : 0, row = q * 32 + lane;
-  const bool reader = N == 32 ? (warp & 2) == 0 : warp < 2;
+  // read-back.  An M = 64 accumulator keeps row r at TMEM lane 32 (r / 16) + r % 16: warp w reads lane quarter w % 4, i.e. rows
+  // 16 (w % 4) + lane for lane < 16, and 16 columns (N = 32: all eight warps; N = 16: warps 0-3).
+  // (M = 128 MMAs over the same tiles -- upper 64 rows garbage -- take 40 instead of 24 cycles each: the A fetch from shared
+  // memory paces them.)
+  const int q = warp & 3, c0 = N == 32 ? (warp >> 2) * 16 : 0, row = lane < 16 ? q * 16 + lane : 64;
+  const bool reader = N == 32 ? true : warp < 4;
   if (reader) {
     float4 b4[4];
 #pragma unroll
@@ -628,6 +642,7 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
     ptx::mbar_wait(st.dbar, st.pd);
     __syncwarp();
     ptx::tc_fence_after();
+    if (warp == 0) after_mma();
     if (tr && threadIdx.x == 0) tr[5] = clock64();
     uint32_t r[16];
     ptx::tmem_ld16(st.tmem + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
@@ -711,8 +726,8 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     ptx::tmem_alloc(ptx::smem_u32(&s_tmem), 256);
     ptx::tmem_relinquish();
   }
-  // the 8 KB behind the last A chunk are read (never used) by the M = 128 MMAs: give them defined contents once
-  for (int i = tid; i < (kTcABytes + kTcWBytes + 8192) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (kTcABytes + kTcWBytes) / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async_smem();   // ... before the TMA unit writes there
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -722,6 +737,9 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
   const CUtensorMap* __restrict__ wm = p.wmaps;   // [layer][qkv, out, fc1, fc2]
   const bool qkv_cta = cta < 96, out_cta = cta < 64;   // 3072 / 32 and 1024 / 16 column slices
 
+  // A phase's weight boxes are issued one phase ahead wherever a phase without weights sits in between (attention, LayerNorm):
+  // they have left the TMA queue by the time the phase's A boxes enter it
+  if (qkv_cta) tc_issue_w<32>(st, wm + 0, 0, cta * 32);
   if (cta < R) ln_row(p, cta, nullptr, 0, L[0].g1, L[0].be1, false, p.xn, nullptr, s_red);
 
   for (int l = 0; l < p.n_layers; ++l) {
@@ -729,31 +747,32 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     const bool last = l + 1 == p.n_layers;
     // ---- q, k, v = LN1(x) Wqkv^T + b: 32 columns per CTA, 96 CTAs
     STAMP(0);
-    TC_BARRIER(if (qkv_cta) tc_issue_w<32>(st, wm + 4 * l + 0, 0, cta * 32); if (tid == 0) ptx::prefetch_tmap(&map_xn));
+    TC_BARRIER((void)0);
     STAMP(1);
     if (qkv_cta)
       tc_gemm_phase<32>(st, &map_xn, 0, R, W.bqkv + cta * 32, p.flags, TR(0), [&](int row, int c0, const float (&v)[16]) {
         store16_bf16(p.qkv + (size_t)row * 3072 + cta * 32 + c0, v);
-      });
+      }, [] {});
     STAMP(4);
-    TC_BARRIER((void)0);
+    TC_BARRIER(if (out_cta) tc_issue_w<16>(st, wm + 4 * l + 1, 0, cta * 16));   // lands during the attention phase
     STAMP(5);
     attention_phase_mma(p, smem, TR(4));
     STAMP(6);
     // ---- attention output projection: 16 columns per CTA, 64 CTAs, partial slot 0 (bias / residual: LayerNorm phase)
-    TC_BARRIER(if (out_cta) tc_issue_w<16>(st, wm + 4 * l + 1, 0, cta * 16); if (tid == 0) ptx::prefetch_tmap(&map_att));
+    TC_BARRIER((void)0);
     STAMP(7);
     if (out_cta)
       tc_gemm_phase<16>(st, &map_att, 0, R, nullptr, p.flags, TR(1), [&](int row, int c0, const float (&v)[16]) {
         store16_f32(p.part + (size_t)row * 1024 + cta * 16 + c0, v);
-      });
+      }, [] {});
     STAMP(10);
-    TC_BARRIER((void)0);
+    LnWeights lw;   // the LayerNorm phases' weights are fetched (from HBM) under the barrier in front of them
+    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 2, 0, cta * 32); if (cta < R) lw = ln_weights(W.bo, W.g2, W.be2));   // W1 lands during the LayerNorm phase
     STAMP(11);
-    if (cta < R) ln_row(p, cta, W.bo, 1, W.g2, W.be2, true, p.xn, nullptr, s_red);
+    if (cta < R) ln_row(p, cta, lw, 1, true, p.xn, nullptr, s_red);
     STAMP(12);
     // ---- h = GELU(LN2(x) W1^T + b1): 32 columns per CTA
-    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 2, 0, cta * 32); if (tid == 0) ptx::prefetch_tmap(&map_xn));
+    TC_BARRIER((void)0);
     STAMP(13);
     tc_gemm_phase<32>(st, &map_xn, 0, R, W.b1 + cta * 32, p.flags, TR(2), [&](int row, int c0, const float (&v)[16]) {
       float y[16];
@@ -764,20 +783,21 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
         y[i + 1] = g.y;
       }
       store16_bf16(p.h + (size_t)row * 4096 + cta * 32 + c0, y);
-    });
+    }, [&] { tc_issue_w<32>(st, wm + 4 * l + 3, (cta >> 5) * 1024, (cta & 31) * 32); });   // fc2's weights: no phase in between to hide them
     STAMP(16);
     // ---- fc2: 32 columns x one quarter of K = 4096 per CTA, partial slot = K quarter
-    TC_BARRIER(tc_issue_w<32>(st, wm + 4 * l + 3, (cta >> 5) * 1024, (cta & 31) * 32); if (tid == 0) ptx::prefetch_tmap(&map_h));
+    TC_BARRIER((void)0);
     STAMP(17);
     tc_gemm_phase<32>(st, &map_h, (cta >> 5) * 1024, R, nullptr, p.flags, TR(3), [&](int row, int c0, const float (&v)[16]) {
       store16_f32(p.part + ((size_t)(cta >> 5) * R + row) * 1024 + (cta & 31) * 32 + c0, v);
-    });
+    }, [] {});
     STAMP(20);
-    TC_BARRIER((void)0);
+    TC_BARRIER(if (!last && qkv_cta) tc_issue_w<32>(st, wm + 4 * (l + 1) + 0, 0, cta * 32);   /* next layer's Wqkv */
+               if (cta < R) lw = last ? ln_weights(W.b2, p.gF, p.bF) : ln_weights(W.b2, L[l + 1].g1, L[l + 1].be1));
     STAMP(21);
     if (cta < R) {
-      if (last) ln_row(p, cta, W.b2, 4, p.gF, p.bF, false, nullptr, p.feats, s_red);
-      else ln_row(p, cta, W.b2, 4, L[l + 1].g1, L[l + 1].be1, true, p.xn, nullptr, s_red);
+      if (last) ln_row(p, cta, lw, 4, false, nullptr, p.feats, s_red);
+      else ln_row(p, cta, lw, 4, true, p.xn, nullptr, s_red);
     }
     STAMP(22);
   }

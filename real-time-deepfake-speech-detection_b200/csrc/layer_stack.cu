@@ -576,6 +576,7 @@ struct TcState {
   uint32_t abar, wbar, dbar;   // mbarriers: A landed (one per issuer, 8 bytes apart), W landed, MMAs retired (count = issuers)
   uint32_t tmem;               // accumulator base (32 columns per issuer)
   uint32_t pa, pw, pd;         // their phase parities (uniform over the CTA)
+  int big;                     // tensor maps are the 3-D (columns, rows, k-chunks) kind: one TMA box per operand slice
 };
 
 // lanes 0-15 of warp 0, in the gap of the grid barrier in front of the phase: this CTA's weight rows [n0, n0 + N) x [k0, k0 + 1024)
@@ -584,7 +585,11 @@ __device__ __forceinline__ void tc_issue_w(const TcState& st, const CUtensorMap*
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0) ptx::mbar_expect_tx(st.wbar, 16u * N * 128u);
     __syncwarp();
-    if (threadIdx.x < 16) ptx::tma_load_2d(st.sW + threadIdx.x * N * 128, map, st.wbar, k0 + threadIdx.x * 64, n0);
+    if (st.big) {   // one box: 64 columns x N rows x 16 k-chunks
+      if (threadIdx.x == 0) ptx::tma_load_3d(st.sW, map, st.wbar, 0, n0, k0 >> 6);
+    } else if (threadIdx.x < 16) {
+      ptx::tma_load_2d(st.sW + threadIdx.x * N * 128, map, st.wbar, k0 + threadIdx.x * 64, n0);
+    }
   }
 }
 
@@ -602,10 +607,18 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
     // proxy fence orders them before the async-proxy (TMA) reads below
     // (restricted to the global space: the unrestricted form costs 800 cycles more per phase, profiles/r02_layer_stack.txt)
     if (!(flags & 1)) asm volatile("fence.proxy.async.global;" ::: "memory");
-    const uint32_t mybar = st.abar + 8 * (threadIdx.x / per);
-    if (threadIdx.x % per == 0) ptx::mbar_expect_tx(mybar, (uint32_t)per * 8192u);
-    __syncwarp(0xffffu);
-    ptx::tma_load_2d(st.sA + threadIdx.x * 8192, mapA, mybar, k0 + threadIdx.x * 64, 0);
+    if (st.big) {   // one box per issuer: 64 columns x 64 rows x `per` k-chunks
+      if (threadIdx.x < ni) {
+        const uint32_t mybar = st.abar + 8 * threadIdx.x;
+        ptx::mbar_expect_tx(mybar, (uint32_t)per * 8192u);
+        ptx::tma_load_3d(st.sA + threadIdx.x * per * 8192, mapA, mybar, 0, 0, (k0 >> 6) + threadIdx.x * per);
+      }
+    } else {
+      const uint32_t mybar = st.abar + 8 * (threadIdx.x / per);
+      if (threadIdx.x % per == 0) ptx::mbar_expect_tx(mybar, (uint32_t)per * 8192u);
+      __syncwarp(0xffffu);
+      ptx::tma_load_2d(st.sA + threadIdx.x * 8192, mapA, mybar, k0 + threadIdx.x * 64, 0);
+    }
     if (tr && threadIdx.x == 0) tr[1] = clock64();
   }
   // MMA issuers: lane 0 of warps 0 .. ni-1, each over its own k-chunks into its own accumulator (columns 32 i ..): one thread
@@ -712,6 +725,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
   st.wbar = ptx::smem_u32(&s_bars[8]);
   st.dbar = ptx::smem_u32(&s_bars[9]);
   st.pa = st.pw = st.pd = 0;
+  st.big = p.big_boxes;
   if (tid == 0) {
     s_abort = 0;
     for (int i = 0; i < 8; ++i) ptx::mbar_init(st.abar + 8 * i, 1);
@@ -821,19 +835,43 @@ finish:
 
 }  // namespace
 
-int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtensorMap* host_out) {
-  for (int l = 0; l < n_layers; ++l) {
-    const bf16* w[4] = {host_layers[l].wqkv, host_layers[l].wo, host_layers[l].w1, host_layers[l].w2};
-    const uint64_t n[4] = {3072, 1024, 4096, 1024}, k[4] = {1024, 1024, 1024, 4096};
-    const uint32_t rows[4] = {32, 16, 32, 32};
-    for (int i = 0; i < 4; ++i) {
-      const uint64_t dims[2] = {k[i], n[i]};
-      const uint64_t strides[1] = {k[i] * 2};
-      const uint32_t box[2] = {64, rows[i]};
-      RTDF_TRY(make_tmap_bf16(&host_out[4 * l + i], w[i], 2, dims, strides, box, TMAP_SW128));
-    }
+// bf16 matrix [rows][k] as a TMA tensor: 3-D (64 columns, rows, k / 64 chunks) with boxes of (64, box_rows, box_chunks) -- the
+// chunk dimension's stride (128 B) is smaller than the row stride, which the encoder accepts on the drivers this was run on --
+// or plain 2-D (k, rows) with boxes of (64, box_rows)
+static int stack_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows, uint32_t box_chunks, bool big) {
+  if (big) {
+    const uint64_t dims[3] = {64, rows, k / 64};
+    const uint64_t strides[2] = {k * 2, 128};
+    const uint32_t box[3] = {64, box_rows, box_chunks};
+    return make_tmap_bf16(out, base, 3, dims, strides, box, TMAP_SW128);
   }
-  return RTDF_OK;
+  const uint64_t dims[2] = {k, rows};
+  const uint64_t strides[1] = {k * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return make_tmap_bf16(out, base, 2, dims, strides, box, TMAP_SW128);
+}
+
+int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtensorMap* host_out, int* big_boxes) {
+  static int want = -1;   // RTDF_STACK_BOXES=small: one 2-D box per k-chunk (A/B timing; also the automatic choice if the 3-D encode fails)
+  if (want < 0) {
+    const char* e = getenv("RTDF_STACK_BOXES");
+    want = (e && e[0] == 's') ? 0 : 1;
+  }
+  for (int big = want; big >= 0; --big) {
+    int rc = RTDF_OK;
+    for (int l = 0; l < n_layers && rc == RTDF_OK; ++l) {
+      const bf16* w[4] = {host_layers[l].wqkv, host_layers[l].wo, host_layers[l].w1, host_layers[l].w2};
+      const uint64_t n[4] = {3072, 1024, 4096, 1024}, k[4] = {1024, 1024, 1024, 4096};
+      const uint32_t rows[4] = {32, 16, 32, 32};
+      for (int i = 0; i < 4 && rc == RTDF_OK; ++i) rc = stack_tmap(&host_out[4 * l + i], w[i], n[i], k[i], rows[i], 16, big != 0);
+    }
+    if (rc == RTDF_OK) {
+      *big_boxes = big;
+      return RTDF_OK;
+    }
+    if (big == 0) return rc;
+  }
+  return RTDF_ERR_CUDA;
 }
 
 static int stack_impl() {   // RTDF_STACK_IMPL=mma: the mma.sync variant (A/B timing)
@@ -872,15 +910,10 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
     RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&layer_stack_mma_kernel), (size_t)kSmemBytes));
     layer_stack_mma_kernel<<<kCtas, kThreads, kSmemBytes, s>>>(q);
   } else {
-    CUtensorMap maps[3];   // activations as (K, R) bf16 tensors; box = 64 columns x 64 rows (one k-chunk of the A operand)
+    CUtensorMap maps[3];   // activations [R][k]: boxes of 64 columns x 64 rows (x 2 k-chunks = one MMA issuer's share)
     const void* base[3] = {p.xn, p.att, p.h};
     const int kdim[3] = {1024, 1024, 4096};
-    for (int i = 0; i < 3; ++i) {
-      const uint64_t dims[2] = {(uint64_t)kdim[i], (uint64_t)p.R};
-      const uint64_t strides[1] = {(uint64_t)kdim[i] * 2};
-      const uint32_t box[2] = {64, 64};
-      RTDF_TRY(make_tmap_bf16(&maps[i], base[i], 2, dims, strides, box, TMAP_SW128));
-    }
+    for (int i = 0; i < 3; ++i) RTDF_TRY(stack_tmap(&maps[i], base[i], (uint64_t)p.R, (uint64_t)kdim[i], 64, 16 / kTcIssuers, p.big_boxes != 0));
     RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&layer_stack_tc_kernel), (size_t)kTcSmemBytes));
     layer_stack_tc_kernel<<<kCtas, kThreads, kTcSmemBytes, s>>>(q, maps[0], maps[1], maps[2]);
   }

@@ -28,6 +28,7 @@ struct StackParams {
   unsigned* sync;             // [2] device words, zero between launches (the kernel resets them on its way out)
   int* fault;                 // mapped host word: set if a grid barrier timed out
   const CUtensorMap* wmaps = nullptr;    // device array [n_layers][4]: TMA maps of wqkv, wo, w1, w2 (layer_stack_build_wmaps)
+  int big_boxes = 0;                     // wmaps are the 3-D kind (as reported by layer_stack_build_wmaps)
   int flags = 0;                         // debug A/B switches (RTDF_STACK_FLAGS)
   unsigned long long* trace = nullptr;   // debug: phase time stamps (RTDF_STACK_TRACE=1)
 };
@@ -39,8 +40,9 @@ constexpr int kStackMaxRows = 64;
 // mma.sync B fragments).  Not a PDL launch; safe inside stream capture.
 int layer_stack_bf16(cudaStream_t s, const StackParams& p);
 
-// host_out[4 * l + {0,1,2,3}] = TMA maps of layer l's wqkv, wo, w1, w2 (boxes of 64 k x 32 / 16 / 32 / 32 rows); the caller
-// copies the array to device memory (64-byte aligned) and passes it as StackParams::wmaps.
-int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtensorMap* host_out);
+// host_out[4 * l + {0,1,2,3}] = TMA maps of layer l's wqkv, wo, w1, w2 (a CTA's slice = 32 / 16 / 32 / 32 rows x 1024 columns: one
+// 3-D box, or sixteen 2-D boxes if the 3-D encode is refused -> *big_boxes); the caller copies the array to device memory
+// (64-byte aligned) and passes it as StackParams::wmaps with StackParams::big_boxes.
+int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtensorMap* host_out, int* big_boxes);
 
 }  // namespace rtdf

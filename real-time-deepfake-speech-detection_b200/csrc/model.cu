@@ -1022,6 +1022,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     sp.gF = c->enc_ln.g;
     sp.bF = c->enc_ln.b;
     sp.wmaps = c->stack_wmaps;
+    sp.big_boxes = c->stack_big_boxes;
     sp.sync = c->stack_sync;
     sp.fault = c->stack_fault;
     return layer_stack_bf16(s, sp);
@@ -1534,7 +1535,7 @@ int rtdf_finalize(rtdf_ctx* c) {
     c->stack_layers = static_cast<rtdf::StackLayer*>(dev);
     {
       std::vector<CUtensorMap> maps(4 * host.size());
-      RTDF_TRY(rtdf::layer_stack_build_wmaps(host.data(), (int)host.size(), maps.data()));
+      RTDF_TRY(rtdf::layer_stack_build_wmaps(host.data(), (int)host.size(), maps.data(), &c->stack_big_boxes));
       void* dm = nullptr;
       RTDF_CHECK_CUDA(cudaMalloc(&dm, maps.size() * sizeof(CUtensorMap)));
       c->owned.push_back(dm);

@@ -852,11 +852,9 @@ static int stack_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 
 int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtensorMap* host_out, int* big_boxes) {
-  static int want = -1;   // RTDF_STACK_BOXES=small: one 2-D box per k-chunk (A/B timing; also the automatic choice if the 3-D encode fails)
-  if (want < 0) {
-    const char* e = getenv("RTDF_STACK_BOXES");
-    want = (e && e[0] == 's') ? 0 : 1;
-  }
+  // RTDF_STACK_BOXES=small (read per context): one 2-D box per k-chunk (A/B timing; also the automatic choice if the 3-D encode fails)
+  const char* e = getenv("RTDF_STACK_BOXES");
+  const int want = (e && e[0] == 's') ? 0 : 1;
   for (int big = want; big >= 0; --big) {
     int rc = RTDF_OK;
     for (int l = 0; l < n_layers && rc == RTDF_OK; ++l) {
@@ -872,15 +870,6 @@ int layer_stack_build_wmaps(const StackLayer* host_layers, int n_layers, CUtenso
     if (big == 0) return rc;
   }
   return RTDF_ERR_CUDA;
-}
-
-static int stack_impl() {   // RTDF_STACK_IMPL=mma: the mma.sync variant (A/B timing)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RTDF_STACK_IMPL");
-    v = (e && e[0] == 'm') ? 1 : 0;
-  }
-  return v;
 }
 
 int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
@@ -906,7 +895,7 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
     RTDF_CHECK_CUDA(cudaMemsetAsync(t, 0, 104 * sizeof(unsigned long long), s));
     q.trace = static_cast<unsigned long long*>(t);
   }
-  if (stack_impl() == 1) {
+  if (p.impl == 1) {
     RTDF_CHECK_CUDA(raise_max_dyn_smem(reinterpret_cast<const void*>(&layer_stack_mma_kernel), (size_t)kSmemBytes));
     layer_stack_mma_kernel<<<kCtas, kThreads, kSmemBytes, s>>>(q);
   } else {

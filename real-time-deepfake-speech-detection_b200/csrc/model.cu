@@ -1023,6 +1023,7 @@ static int run_frontend(rtdf_ctx* c, cudaStream_t s, const float* wav, const Dim
     sp.bF = c->enc_ln.b;
     sp.wmaps = c->stack_wmaps;
     sp.big_boxes = c->stack_big_boxes;
+    sp.impl = c->stack_impl;
     sp.sync = c->stack_sync;
     sp.fault = c->stack_fault;
     return layer_stack_bf16(s, sp);
@@ -1457,6 +1458,8 @@ int rtdf_create(rtdf_ctx** out, int device, const rtdf_model_desc* desc) {
   {  // RTDF_LAYER_STACK=0: streaming chunks of <= 64 frames keep the kernel-per-op chain instead of the persistent layer-stack kernel
     const char* e = getenv("RTDF_LAYER_STACK");
     c->layer_stack = !(e && e[0] == '0') && c->d.precision == RTDF_PREC_BF16 && !c->ln_fold;
+    e = getenv("RTDF_STACK_IMPL");   // mma: its mma.sync variant (A/B timing)
+    c->stack_impl = (e && e[0] == 'm') ? 1 : 0;
   }
   {  // second stream + fork / join events for the independent graph branches of the AASIST back-end (RTDF_BRANCH_STREAMS=0: off)
     const char* e = getenv("RTDF_BRANCH_STREAMS");

@@ -133,6 +133,7 @@ struct rtdf_ctx {
   bool layer_stack = false;                  // RTDF_LAYER_STACK (read at rtdf_create)
   rtdf::StackLayer* stack_layers = nullptr;  // device array of per-layer pointers (built by rtdf_finalize)
   CUtensorMap* stack_wmaps = nullptr;        // device array [layers][4] of weight tensor maps
+  int stack_impl = 0;                        // RTDF_STACK_IMPL (read at rtdf_create): 0 = tcgen05, 1 = mma.sync variant
   int stack_big_boxes = 0;                   // ... of the 3-D kind (one TMA box per operand slice)
   unsigned* stack_sync = nullptr;            // its grid-barrier words
   int* stack_fault = nullptr;                // mapped host word the kernel sets when a barrier times out

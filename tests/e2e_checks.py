@@ -170,13 +170,19 @@ def check_layer_stack():
     out["conformer_b1_1s"] = check_e2e("ConformerModel", "bf16", B=1, N=16000)
     for B, N in ((2, 8000), (4, 5200), (1, 20800), (3, 3000), (1, 1000)):                  # 48, 64, 64, 27, 2 rows
         out[f"feats_b{B}_n{N}"] = check_frontend_block("bf16", B=B, N=N, kind="My_XLSR_AASIST", num_layers=3, order="first")
-    # same model through both paths
-    os.environ["RTDF_LAYER_STACK"] = "0"
-    try:
-        _, chain = build_pair("My_XLSR_AASIST", "bf16", num_layers=4, order="first")
-        chain.engine()
-    finally:
-        del os.environ["RTDF_LAYER_STACK"]
+    # same model through the kernel-per-op chain, the tcgen05 layer-stack kernel (default) and its mma.sync variant
+    def with_env(**env):
+        os.environ.update(env)
+        try:
+            _, m = build_pair("My_XLSR_AASIST", "bf16", num_layers=4, order="first")
+            m.engine()
+        finally:
+            for k in env:
+                del os.environ[k]
+        return m
+    chain = with_env(RTDF_LAYER_STACK="0")
+    mma = with_env(RTDF_STACK_IMPL="mma")
+    small = with_env(RTDF_STACK_BOXES="small")
     _, stack = build_pair("My_XLSR_AASIST", "bf16", num_layers=4, order="first")
     stack.engine()
     x = _waves(1, 16000, seed=11).cuda()
@@ -187,8 +193,10 @@ def check_layer_stack():
     n2 = lib.rtdf_launch_count()
     out["launches_stack"], out["launches_chain"] = int(n1 - n0), int(n2 - n1)
     out["stack_vs_chain"] = float((a - b).abs().max())
+    out["mma_vs_chain"] = float((mma(x) - b).abs().max())
     assert out["launches_chain"] - out["launches_stack"] >= 4 * 6, out      # >= 7 kernels per layer replaced by one launch
-    assert out["stack_vs_chain"] <= TOL["bf16"], out
+    assert out["stack_vs_chain"] <= TOL["bf16"] and out["mma_vs_chain"] <= TOL["bf16"], out
+    assert torch.equal(small(x), a), "2-D and 3-D TMA boxes must give identical results"
     for _ in range(5):
         assert torch.equal(stack(x), a), "layer-stack replays differ"
     return out

@@ -6,14 +6,20 @@
 //
 //     LN1 | QKV | attention | out_proj | +x, LN2 | fc1 + GELU | fc2 (K split in 4) | +x, LN1 of the next layer | ...
 //
-// with a grid-wide barrier (one release-add + acquire-poll on a global word) between them.  A GEMM phase gives each CTA an
-// 8 - 32 column slice of the output over K = 1024: the activations (<= 64 rows x 1024, bf16) are copied to shared memory in
-// mma.sync A-fragment order with cp.async, the weights never touch shared memory -- every thread loads its B fragments for
-// the whole phase as 16-byte global loads (8 consecutive k of one weight row; the k permutation inside a 32-wide block is
-// applied to A and B alike, so the products pair up correctly) BEFORE the barrier in front of the phase, which hides the HBM
-// latency behind the barrier and the previous phase's tail.  The 8 warps split K; their partial tiles are summed through
-// shared memory in warp order, fc2's four K chunks through global partials in chunk order: results are deterministic.
-// Attention (<= 64 keys) is fp32 SIMT: (utterance, head, query split) items, one query row per warp at a time.
+// with a grid-wide barrier (one release-add + acquire-poll on a global word, in an arrive and a wait half) between them.
+// Everything is summed in a fixed order (accumulators in index order, fc2's four K chunks through global partials in chunk
+// order): replays are bit-identical.  A barrier that never completes (a CTA that is not resident) makes the kernel return and
+// set a host-visible flag; the next forward call raises.
+//
+// Two variants of the GEMM phases (a CTA = an 8 - 32 column slice of the output over K = 1024):
+//   * layer_stack_tc_kernel (default, second half of this file): TMA boxes + tcgen05 MMAs, mma.sync attention;
+//   * layer_stack_mma_kernel (RTDF_STACK_IMPL=mma, the first version, kept for A/B timing): the activations are copied to
+//     shared memory in mma.sync A-fragment order with cp.async, the weights never touch shared memory -- every thread loads
+//     its B fragments for the whole phase as 16-byte global loads (8 consecutive k of one weight row; the k permutation inside
+//     a 32-wide block is applied to A and B alike, so the products pair up correctly) between the two halves of the barrier in
+//     front of the phase.  The 8 warps split K; their partial tiles are summed through shared memory in warp order.
+//     Attention is fp32 SIMT: (utterance, head, query split) items, one query row per warp at a time.
+// Measurements of every step: profiles/r02_layer_stack.txt.
 #include "layer_stack.cuh"
 
 #include "ptx.cuh"
@@ -598,7 +604,7 @@ __device__ __forceinline__ void tc_issue_w(const TcState& st, const CUtensorMap*
 // after_mma(): runs in warp 0 once this phase's MMAs have retired (the weight buffer is free again), ahead of the read-back.
 template <int N, class Epi, class After>
 __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* mapA, int k0, int R, const float* __restrict__ bias,
-                                              int flags, unsigned long long* tr, Epi epi, After after_mma) {
+                                              unsigned long long* tr, Epi epi, After after_mma) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ni = kTcIssuers, per = 16 / ni;   // MMA issuers, k-chunks per issuer
   if (threadIdx.x < 16) {   // one A box (k-chunk) per lane; the chunks of issuer i complete on mbarrier abar + 8 i
@@ -606,7 +612,7 @@ __device__ __forceinline__ void tc_gemm_phase(TcState& st, const CUtensorMap* ma
     // the rows were written by other CTAs' generic-proxy stores and are ordered before this point by the grid barrier; the
     // proxy fence orders them before the async-proxy (TMA) reads below
     // (restricted to the global space: the unrestricted form costs 800 cycles more per phase, profiles/r02_layer_stack.txt)
-    if (!(flags & 1)) asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     if (st.big) {   // one box per issuer: 64 columns x 64 rows x `per` k-chunks
       if (threadIdx.x < ni) {
         const uint32_t mybar = st.abar + 8 * threadIdx.x;
@@ -764,7 +770,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     TC_BARRIER((void)0);
     STAMP(1);
     if (qkv_cta)
-      tc_gemm_phase<32>(st, &map_xn, 0, R, W.bqkv + cta * 32, p.flags, TR(0), [&](int row, int c0, const float (&v)[16]) {
+      tc_gemm_phase<32>(st, &map_xn, 0, R, W.bqkv + cta * 32, TR(0), [&](int row, int c0, const float (&v)[16]) {
         store16_bf16(p.qkv + (size_t)row * 3072 + cta * 32 + c0, v);
       }, [] {});
     STAMP(4);
@@ -776,7 +782,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     TC_BARRIER((void)0);
     STAMP(7);
     if (out_cta)
-      tc_gemm_phase<16>(st, &map_att, 0, R, nullptr, p.flags, TR(1), [&](int row, int c0, const float (&v)[16]) {
+      tc_gemm_phase<16>(st, &map_att, 0, R, nullptr, TR(1), [&](int row, int c0, const float (&v)[16]) {
         store16_f32(p.part + (size_t)row * 1024 + cta * 16 + c0, v);
       }, [] {});
     STAMP(10);
@@ -788,7 +794,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     // ---- h = GELU(LN2(x) W1^T + b1): 32 columns per CTA
     TC_BARRIER((void)0);
     STAMP(13);
-    tc_gemm_phase<32>(st, &map_xn, 0, R, W.b1 + cta * 32, p.flags, TR(2), [&](int row, int c0, const float (&v)[16]) {
+    tc_gemm_phase<32>(st, &map_xn, 0, R, W.b1 + cta * 32, TR(2), [&](int row, int c0, const float (&v)[16]) {
       float y[16];
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
@@ -802,7 +808,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     // ---- fc2: 32 columns x one quarter of K = 4096 per CTA, partial slot = K quarter
     TC_BARRIER((void)0);
     STAMP(17);
-    tc_gemm_phase<32>(st, &map_h, (cta >> 5) * 1024, R, nullptr, p.flags, TR(3), [&](int row, int c0, const float (&v)[16]) {
+    tc_gemm_phase<32>(st, &map_h, (cta >> 5) * 1024, R, nullptr, TR(3), [&](int row, int c0, const float (&v)[16]) {
       store16_f32(p.part + ((size_t)(cta >> 5) * R + row) * 1024 + (cta & 31) * 32 + c0, v);
     }, [] {});
     STAMP(20);
@@ -881,13 +887,7 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
     const char* e = getenv("RTDF_STACK_TRACE");
     trace_mode = (e && e[0] == '1') ? 1 : 0;
   }
-  static int dbg_flags = -1;    // RTDF_STACK_FLAGS (debug A/B): 1 = no proxy fence in front of the A boxes
-  if (dbg_flags < 0) {
-    const char* e = getenv("RTDF_STACK_FLAGS");
-    dbg_flags = e ? atoi(e) : 0;
-  }
   StackParams q = p;
-  q.flags = dbg_flags;
   q.trace = nullptr;
   if (trace_mode) {
     void* t = nullptr;

@@ -30,7 +30,6 @@ struct StackParams {
   const CUtensorMap* wmaps = nullptr;    // device array [n_layers][4]: TMA maps of wqkv, wo, w1, w2 (layer_stack_build_wmaps)
   int impl = 0;                          // 0 = tcgen05 GEMM phases (default), 1 = mma.sync variant (RTDF_STACK_IMPL=mma, A/B timing)
   int big_boxes = 0;                     // wmaps are the 3-D kind (as reported by layer_stack_build_wmaps)
-  int flags = 0;                         // debug A/B switches (RTDF_STACK_FLAGS)
   unsigned long long* trace = nullptr;   // debug: phase time stamps (RTDF_STACK_TRACE=1)
 };
 

@@ -565,12 +565,14 @@ __device__ __forceinline__ void attention_phase_mma(const StackParams& p, unsign
 
 // =====================================================================================================================
 // tcgen05 variant (default): the GEMM phases on the 5th-generation tensor cores.
-//   A (<= 64 rows x 1024, bf16) arrives as 16 TMA boxes of 64 rows x 64 columns (128-byte swizzled rows; rows >= R are
-//   zero-filled by the TMA unit), the CTA's weight slice (32 or 16 rows x 1024) as 16 boxes issued one grid barrier EARLIER
-//   or one whole phase earlier), so the HBM stream runs under the barrier / the attention or LayerNorm phase.  Eight threads
-//   issue 8 MMAs each (M = 64, N = 32 | 16, K = 16) over their own two k-chunks into their own accumulator (32 columns of
-//   tensor memory each) -- a single thread paces such small MMAs at ~50 cycles apiece, the tensor pipe takes them at ~24 --
-//   and the read-back sums the eight accumulators in order: no weight registers, no shared-memory reduction.
+//   A (<= 64 rows x 1024, bf16) arrives as eight TMA boxes of 64 rows x 2 k-chunks of 64 columns (128-byte swizzled rows; rows
+//   >= R are zero-filled by the TMA unit), the CTA's weight slice (32 or 16 rows x 1024) as ONE box issued between the two
+//   halves of the grid barrier in front of the phase or -- where an attention / LayerNorm phase sits in between -- a whole
+//   phase earlier, so the HBM stream runs under the barriers.  (3-D tensor maps (column, row, k-chunk); sixteen 2-D boxes per
+//   slice if the driver refuses them.)  Eight threads issue 8 MMAs each (M = 64, N = 32 | 16, K = 16) over their own two
+//   k-chunks into their own accumulator (32 columns of tensor memory each) -- a single thread paces such small MMAs at ~50
+//   cycles apiece, the tensor pipe takes them at ~24 -- and the read-back sums the eight accumulators in order: no weight
+//   registers, no shared-memory reduction.
 // =====================================================================================================================
 constexpr int kTcABytes = 16 * 8192;                   // 16 k-chunks x (64 rows x 128 B)
 constexpr int kTcWBytes = 16 * 32 * 128;               // 16 k-chunks x (32 rows x 128 B)
@@ -585,7 +587,8 @@ struct TcState {
   int big;                     // tensor maps are the 3-D (columns, rows, k-chunks) kind: one TMA box per operand slice
 };
 
-// lanes 0-15 of warp 0, in the gap of the grid barrier in front of the phase: this CTA's weight rows [n0, n0 + N) x [k0, k0 + 1024)
+// warp 0, between the two halves of a grid barrier (or right after the previous phase's MMAs): this CTA's weight rows
+// [n0, n0 + N) x [k0, k0 + 1024) -> sW
 template <int N>
 __device__ __forceinline__ void tc_issue_w(const TcState& st, const CUtensorMap* map, int k0, int n0) {
   if (threadIdx.x < 32) {

@@ -72,15 +72,20 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
 // round are in (wait).  Between the halves the threads issue the weight loads of the next GEMM phase, so the HBM stream runs
 // under the barrier.  wait: false = gave up (a CTA never arrived: the grid was not co-resident); the kernel then returns and
 // the host finds the flag.
-__device__ __forceinline__ void barrier_arrive(const StackParams& p, unsigned& target) {
+__device__ __forceinline__ void barrier_arrive(const StackParams& p, unsigned& target, unsigned long long* tr = nullptr) {
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (tr) tr[1] = clock64();
     target += gridDim.x;
     red_release_gpu_add(p.sync, 1u);
+    if (tr) tr[2] = clock64();
   }
 }
-__device__ __forceinline__ bool barrier_wait(const StackParams& p, unsigned target, volatile int* s_abort) {
+__device__ __forceinline__ bool barrier_wait(const StackParams& p, unsigned target, volatile int* s_abort,
+                                             unsigned long long* tr = nullptr) {
   if (threadIdx.x == 0) {
+    if (tr) tr[3] = clock64();
     unsigned spins = 0;
     while (ld_acquire_gpu(p.sync) < target) {
       if (++spins > kSpinLimit) {
@@ -90,8 +95,13 @@ __device__ __forceinline__ bool barrier_wait(const StackParams& p, unsigned targ
         break;
       }
     }
+    if (tr) {
+      tr[4] = clock64();
+      tr[6] = spins;
+    }
   }
   __syncthreads();
+  if (tr && threadIdx.x == 0) tr[5] = clock64();
   return *s_abort == 0;
 }
 
@@ -589,6 +599,8 @@ struct TcState {
 
 // warp 0, between the two halves of a grid barrier (or right after the previous phase's MMAs): this CTA's weight rows
 // [n0, n0 + N) x [k0, k0 + 1024) -> sW
+// (Issuing a slice BEFORE an arrive -- fc2's weights, right behind fc1's MMAs -- makes that arrive's release wait for the box as
+// well, from whichever warp it is issued: profiles/r02_layer_stack.txt.  It still wins over issuing them behind the arrive.)
 template <int N>
 __device__ __forceinline__ void tc_issue_w(const TcState& st, const CUtensorMap* map, int k0, int n0) {
   if (threadIdx.x < 32) {
@@ -708,12 +720,13 @@ __device__ __forceinline__ void store16_f32(float* dst, const float (&v)[16]) {
 
 // debug trace slots of GEMM phase i (CTA 0, layer 1): 7 stamps each behind the 64 phase-boundary slots
 #define TR(i) ((p.trace && l == 1 && cta == 0) ? p.trace + 64 + 8 * (i) : nullptr)
-#define TC_BARRIER(prefetch)                               \
-  do {                                                     \
-    ptx::fence_proxy_async_smem();                         \
-    barrier_arrive(p, target);                             \
-    prefetch;                                              \
-    if (!barrier_wait(p, target, &s_abort)) goto finish;   \
+#define TC_BARRIER(prefetch)                                    \
+  do {                                                          \
+    ptx::fence_proxy_async_smem();                              \
+    barrier_arrive(p, target, btr);                             \
+    prefetch;                                                   \
+    if (!barrier_wait(p, target, &s_abort, btr)) goto finish;   \
+    btr = nullptr;                                              \
   } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -756,6 +769,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
   ptx::tc_fence_after();
   st.tmem = s_tmem;
   unsigned target = 0;
+  unsigned long long* btr = nullptr;   // debug trace slots of the next barrier
   const StackLayer* __restrict__ L = p.layers;
   const CUtensorMap* __restrict__ wm = p.wmaps;   // [layer][qkv, out, fc1, fc2]
   const bool qkv_cta = cta < 96, out_cta = cta < 64;   // 3072 / 32 and 1024 / 16 column slices
@@ -777,6 +791,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
         store16_bf16(p.qkv + (size_t)row * 3072 + cta * 32 + c0, v);
       }, [] {});
     STAMP(4);
+    btr = TR(6);
     TC_BARRIER(if (out_cta) tc_issue_w<16>(st, wm + 4 * l + 1, 0, cta * 16));   // lands during the attention phase
     STAMP(5);
     attention_phase_mma(p, smem, TR(4));
@@ -809,6 +824,7 @@ layer_stack_tc_kernel(const StackParams p, const __grid_constant__ CUtensorMap m
     }, [&] { tc_issue_w<32>(st, wm + 4 * l + 3, (cta >> 5) * 1024, (cta & 31) * 32); });   // fc2's weights: no phase in between to hide them
     STAMP(16);
     // ---- fc2: 32 columns x one quarter of K = 4096 per CTA, partial slot = K quarter
+    btr = TR(5);
     TC_BARRIER((void)0);
     STAMP(17);
     tc_gemm_phase<32>(st, &map_h, (cta >> 5) * 1024, R, nullptr, TR(3), [&](int row, int c0, const float (&v)[16]) {
@@ -894,8 +910,8 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
   q.trace = nullptr;
   if (trace_mode) {
     void* t = nullptr;
-    RTDF_CHECK_CUDA(cudaMalloc(&t, 104 * sizeof(unsigned long long)));
-    RTDF_CHECK_CUDA(cudaMemsetAsync(t, 0, 104 * sizeof(unsigned long long), s));
+    RTDF_CHECK_CUDA(cudaMalloc(&t, 128 * sizeof(unsigned long long)));
+    RTDF_CHECK_CUDA(cudaMemsetAsync(t, 0, 128 * sizeof(unsigned long long), s));
     q.trace = static_cast<unsigned long long*>(t);
   }
   if (p.impl == 1) {
@@ -911,7 +927,7 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
   }
   RTDF_LAUNCH_CHECK();
   if (trace_mode) {
-    unsigned long long h[104];
+    unsigned long long h[128];
     RTDF_CHECK_CUDA(cudaStreamSynchronize(s));
     RTDF_CHECK_CUDA(cudaMemcpy(h, q.trace, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(q.trace);
@@ -927,6 +943,14 @@ int layer_stack_bf16(cudaStream_t s, const StackParams& p) {
           fprintf(stderr, " %s=%lld", names[i], (long long)(h[c * 32 + i] - h[c * 32 + j]));
         }
       fprintf(stderr, " | layer total %lld\n", (long long)(h[c * 32 + 22] - h[c * 32]));
+    }
+    for (int b = 0; b < 2; ++b) {
+      const unsigned long long* t = h + 104 + 8 * b;
+      if (t[0])
+        fprintf(stderr, "  grid barrier behind the %s phase, CTA 0, cycles from its start: CTA synchronised %lld | arrival sent %lld | "
+                        "polling from %lld | all arrived seen %lld (%llu polls) | CTA released %lld\n", b ? "qkv" : "fc1",
+                (long long)(t[1] - t[0]), (long long)(t[2] - t[0]), (long long)(t[3] - t[0]), (long long)(t[4] - t[0]), t[6],
+                (long long)(t[5] - t[0]));
     }
     if (h[96]) fprintf(stderr, "  attention phase, CTA 0: K / V / Q in shared memory after %lld cycles, rows done after %lld\n",
                        (long long)(h[97] - h[96]), (long long)(h[98] - h[96]));
